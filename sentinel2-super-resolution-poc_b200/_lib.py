@@ -1,0 +1,279 @@
+"""ctypes binding of libwowsr.so (include/wowsr.h).  No CPU fallback: if the library or a CUDA
+device is missing, calls raise."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libwowsr.so")
+
+PREC = {"bf16": 0, "fp16": 1}
+
+
+class PostParams(C.Structure):
+    _fields_ = [("clip_limit", C.c_double), ("sigma", C.c_double), ("alpha", C.c_float), ("beta", C.c_float),
+                ("sat_boost", C.c_float), ("grid", C.c_int32), ("hue_lo", C.c_int32), ("hue_hi", C.c_int32),
+                ("stages", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Image(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("pitch", C.c_int64), ("W", C.c_int32), ("H", C.c_int32),
+                ("y0", C.c_int32), ("rows", C.c_int32)]
+
+
+class Window(C.Structure):
+    _fields_ = [("x0", C.c_int32), ("y0", C.c_int32), ("x1", C.c_int32), ("y1", C.c_int32),
+                ("ox0", C.c_int32), ("oy0", C.c_int32), ("ox1", C.c_int32), ("oy1", C.c_int32)]
+
+
+STAGE_CLAHE, STAGE_UNSHARP, STAGE_VEG, STAGE_ALL = 1, 2, 4, 7
+
+_lib = None
+_lock = threading.Lock()
+
+_SIGS = {
+    "wowsr_abi_version": (C.c_int, []),
+    "wowsr_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "wowsr_destroy": (None, [C.c_void_p]),
+    "wowsr_last_error": (C.c_char_p, [C.c_void_p]),
+    "wowsr_launch_count": (C.c_uint64, [C.c_void_p]),
+    "wowsr_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "wowsr_get_option": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]),
+    "wowsr_post_params_wow": (None, [C.POINTER(PostParams)]),
+    "wowsr_post_params_farm": (None, [C.POINTER(PostParams)]),
+    "wowsr_clahe_hist": (C.c_int, [C.c_void_p, C.POINTER(Image), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "wowsr_clahe_luts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p]),
+    "wowsr_post_apply": (C.c_int, [C.c_void_p, C.POINTER(Image), C.c_void_p, C.POINTER(PostParams), C.c_int32, C.c_int32,
+                                   C.POINTER(Image), C.c_void_p]),
+    "wowsr_post_process_dev": (C.c_int, [C.c_void_p, C.POINTER(Image), C.POINTER(PostParams), C.POINTER(Image), C.c_void_p]),
+    "wowsr_post_process_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(PostParams), C.c_void_p]),
+    "wowsr_clahe_geometry": (None, [C.c_int32, C.c_int32, C.c_int32] + [C.POINTER(C.c_int32)] * 4),
+    "wowsr_get_table": (C.c_int64, [C.c_int32, C.c_void_p, C.c_int64]),
+    "wowsr_gaussian_taps": (C.c_int32, [C.c_double, C.POINTER(C.c_int32), C.c_int32]),
+    "wowsr_plan_windows": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Window), C.c_int32]),
+    "wowsr_load_rrdbnet": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_int32, C.c_int32]),
+    "wowsr_rrdbnet_forward_windows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.POINTER(Window),
+                                                C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
+    "wowsr_enhance_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "wowsr_enhance_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "wowsr_conv3x3_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                     C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "wowsr_get_timing": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float), C.c_int32]),
+    "wowsr_load_edsr": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.POINTER(C.c_void_p), C.c_int32, C.c_int32]),
+    "wowsr_edsr_upsample_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+}
+
+
+def lib():
+    """Loads libwowsr.so (built in-tree by ``__graft_entry__.build()`` / ``make -C csrc``)."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                                   "(there is no CPU fallback)")
+            L = C.CDLL(LIB_PATH)
+            for name, (res, args) in _SIGS.items():
+                fn = getattr(L, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = L
+    return _lib
+
+
+def exported_symbols():
+    return sorted(_SIGS)
+
+
+class WowsrError(RuntimeError):
+    pass
+
+
+class Handle:
+    """One wowsr_ctx bound to a CUDA device."""
+
+    def __init__(self, device: int = 0):
+        self._L = lib()
+        h = C.c_void_p()
+        rc = self._L.wowsr_create(int(device), C.byref(h))
+        if rc != 0:
+            raise WowsrError(f"wowsr_create({device}) failed ({rc}): {self._L.wowsr_last_error(None).decode()}")
+        self._h = h
+        self.device = int(device)
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.wowsr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise WowsrError(f"{what} failed ({rc}): {self._L.wowsr_last_error(self._h).decode()}")
+
+    # -- misc ---------------------------------------------------------------------------------
+    def set_option(self, key: str, value: int):
+        self._check(self._L.wowsr_set_option(self._h, key.encode(), int(value)), "set_option")
+
+    def launch_count(self) -> int:
+        return int(self._L.wowsr_launch_count(self._h))
+
+    def timing(self):
+        buf = (C.c_float * 4)()
+        n = self._L.wowsr_get_timing(self._h, buf, 4)
+        return dict(zip(("total", "head", "trunk", "tail"), list(buf)[:n]))
+
+    # -- post-process -------------------------------------------------------------------------
+    def post_process_host(self, img: np.ndarray, params: PostParams) -> np.ndarray:
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        if img.ndim != 3 or img.shape[2] != 3:
+            raise ValueError("expected HxWx3 uint8")
+        out = np.empty_like(img)
+        self._check(self._L.wowsr_post_process_host(self._h, img.ctypes.data, img.shape[0], img.shape[1], C.byref(params),
+                                                    out.ctypes.data), "post_process_host")
+        return out
+
+    def post_process_dev(self, src_ptr, dst_ptr, H, W, params, stream=0, pitch=None):
+        pitch = pitch or W * 3
+        a = Image(src_ptr, pitch, W, H, 0, H)
+        b = Image(dst_ptr, pitch, W, H, 0, H)
+        self._check(self._L.wowsr_post_process_dev(self._h, C.byref(a), C.byref(params), C.byref(b), C.c_void_p(stream)),
+                    "post_process_dev")
+
+    def clahe_hist(self, image: Image, grid, prow0, prow1, hist_ptr, stream=0):
+        self._check(self._L.wowsr_clahe_hist(self._h, C.byref(image), grid, prow0, prow1, C.c_void_p(hist_ptr), C.c_void_p(stream)),
+                    "clahe_hist")
+
+    def clahe_luts(self, hist_ptr, grid, tw, th, clip, luts_ptr, stream=0):
+        self._check(self._L.wowsr_clahe_luts(self._h, C.c_void_p(hist_ptr), grid, tw, th, float(clip), C.c_void_p(luts_ptr),
+                                             C.c_void_p(stream)), "clahe_luts")
+
+    def post_apply(self, src: Image, luts_ptr, params, row0, row1, dst: Image, stream=0):
+        self._check(self._L.wowsr_post_apply(self._h, C.byref(src), C.c_void_p(luts_ptr), C.byref(params), row0, row1, C.byref(dst),
+                                             C.c_void_p(stream)), "post_apply")
+
+    # -- network ------------------------------------------------------------------------------
+    def load_rrdbnet(self, tensors, num_block, num_feat=64, num_grow=32, precision="bf16"):
+        arrs = [np.ascontiguousarray(t, dtype=np.float32) for t in tensors]
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        self._check(self._L.wowsr_load_rrdbnet(self._h, num_block, num_feat, num_grow, ptrs, len(arrs), PREC[precision]),
+                    "load_rrdbnet")
+
+    def enhance_host(self, img: np.ndarray, tile_size: int, want_float=False):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        H, W = img.shape[:2]
+        out = np.empty((H * 4, W * 4, 3), dtype=np.uint8)
+        outf = np.empty((H * 4, W * 4, 3), dtype=np.float32) if want_float else None
+        self._check(self._L.wowsr_enhance_host(self._h, img.ctypes.data, H, W, tile_size, out.ctypes.data,
+                                               outf.ctypes.data if want_float else None), "enhance_host")
+        return (out, outf) if want_float else out
+
+    def enhance_dev(self, src_ptr, H, W, tile_size, dst_ptr, dst_f32_ptr=None, stream=0):
+        self._check(self._L.wowsr_enhance_dev(self._h, C.c_void_p(src_ptr), H, W, tile_size, C.c_void_p(dst_ptr),
+                                              C.c_void_p(dst_f32_ptr) if dst_f32_ptr else None, C.c_void_p(stream)), "enhance_dev")
+
+    def forward_windows(self, src_ptr, H, W, pitch, windows, dst_ptr, dst_pitch, dst_f32_ptr=None, dst_f32_pitch=0, stream=0):
+        arr = (Window * len(windows))(*windows)
+        self._check(self._L.wowsr_rrdbnet_forward_windows(self._h, C.c_void_p(src_ptr), H, W, pitch, arr, len(windows),
+                                                          C.c_void_p(dst_ptr), dst_pitch,
+                                                          C.c_void_p(dst_f32_ptr) if dst_f32_ptr else None, dst_f32_pitch,
+                                                          C.c_void_p(stream)), "rrdbnet_forward_windows")
+
+    def conv3x3_host(self, x, weight, bias, act=0, precision="bf16"):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        weight = np.ascontiguousarray(weight, dtype=np.float32)
+        bias = np.ascontiguousarray(bias, dtype=np.float32)
+        n, h, w, cin = x.shape
+        cout = weight.shape[0]
+        out = np.empty((n, h, w, cout), dtype=np.float32)
+        self._check(self._L.wowsr_conv3x3_host(self._h, x.ctypes.data, n, h, w, cin, weight.ctypes.data, bias.ctypes.data, cout,
+                                               int(act), PREC[precision], out.ctypes.data), "conv3x3_host")
+        return out
+
+    def load_edsr(self, tensors, num_block=16, num_feat=64, res_scale=1.0, precision="bf16"):
+        arrs = [np.ascontiguousarray(t, dtype=np.float32) for t in tensors]
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        self._check(self._L.wowsr_load_edsr(self._h, num_block, num_feat, float(res_scale), ptrs, len(arrs), PREC[precision]),
+                    "load_edsr")
+
+    def edsr_upsample_host(self, img: np.ndarray, want_float=False):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        H, W = img.shape[:2]
+        out = np.empty((H * 4, W * 4, 3), dtype=np.uint8)
+        outf = np.empty((H * 4, W * 4, 3), dtype=np.float32) if want_float else None
+        self._check(self._L.wowsr_edsr_upsample_host(self._h, img.ctypes.data, H, W, out.ctypes.data,
+                                                     outf.ctypes.data if want_float else None), "edsr_upsample_host")
+        return (out, outf) if want_float else out
+
+
+# -- pure host helpers (no GPU needed) ----------------------------------------------------------
+
+def plan_windows(H, W, tile, pad=10):
+    L = lib()
+    n = L.wowsr_plan_windows(H, W, tile, pad, None, 0)
+    if n < 0:
+        raise ValueError("bad planner arguments")
+    arr = (Window * n)()
+    L.wowsr_plan_windows(H, W, tile, pad, arr, n)
+    return list(arr)
+
+
+def clahe_geometry(H, W, grid=8):
+    v = [C.c_int32() for _ in range(4)]
+    lib().wowsr_clahe_geometry(H, W, grid, *[C.byref(x) for x in v])
+    return tuple(x.value for x in v)  # tile_w, tile_h, padded_w, padded_h
+
+
+def gaussian_taps(sigma):
+    buf = (C.c_int32 * 32)()
+    n = lib().wowsr_gaussian_taps(float(sigma), buf, 32)
+    if n < 0:
+        raise ValueError("sigma too large")
+    return list(buf)[:n]
+
+
+_TABLES = {0: ("gam", np.uint16, 256), 1: ("cbrt", np.uint16, 3072), 2: ("lab_y", np.uint16, 256),
+           3: ("lab_ify", np.uint16, 256), 4: ("invgam", np.uint8, 4096), 5: ("sdiv", np.uint32, 256),
+           6: ("hdiv", np.uint32, 256)}
+
+
+def get_tables():
+    out = {}
+    for tid, (name, dt, n) in _TABLES.items():
+        a = np.empty(n, dtype=dt)
+        got = lib().wowsr_get_table(tid, a.ctypes.data, a.nbytes)
+        if got != a.nbytes:
+            raise RuntimeError(f"table {name}: {got}")
+        out[name] = a
+    return out
+
+
+def post_params(kind="wow", **over) -> PostParams:
+    p = PostParams()
+    (lib().wowsr_post_params_wow if kind == "wow" else lib().wowsr_post_params_farm)(C.byref(p))
+    for k, v in over.items():
+        setattr(p, k, v)
+    return p
+
+
+_handles = {}
+
+
+def default_handle(device: int = 0) -> Handle:
+    with _lock:
+        h = _handles.get(device)
+    if h is None:
+        h = Handle(device)
+        with _lock:
+            _handles[device] = h
+    return h

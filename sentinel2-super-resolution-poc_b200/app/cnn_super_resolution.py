@@ -1,0 +1,188 @@
+"""Drop-in for ``server/app/cnn_super_resolution.py`` (hot-path parts only).
+
+Same public surface as the reference: ``MODELS`` (:28-45), ``get_model_dir`` / ``download_weights``
+(:48-70), ``RRDBNet`` (:110-158, here a parameter container with the official state_dict keys) and
+``RealESRGAN(scale, device, tile_size, model_name).enhance(img)`` (:161-280).  The forward pass, the
+tile planner and the stitching run in libwowsr.so on the GPU.
+"""
+from __future__ import annotations
+
+import urllib.request
+from collections import OrderedDict
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _lib
+
+MODELS = {
+    "realesrgan_x4": {
+        "url": "https://github.com/xinntao/Real-ESRGAN/releases/download/v0.1.0/RealESRGAN_x4plus.pth",
+        "scale": 4, "channels": 64, "blocks": 23, "num_in_ch": 3,
+        "description": "General photos (best quality)",
+    },
+    "realesrgan_anime": {
+        "url": "https://github.com/xinntao/Real-ESRGAN/releases/download/v0.2.2.4/RealESRGAN_x4plus_anime_6B.pth",
+        "scale": 4, "channels": 64, "blocks": 6, "num_in_ch": 3,
+        "description": "Sharp edges (best for text/plates)",
+    },
+}
+
+
+def get_model_dir() -> Path:
+    model_dir = Path(__file__).parent.parent / "models"
+    model_dir.mkdir(exist_ok=True)
+    return model_dir
+
+
+def download_weights(model_name: str) -> Path:
+    """Same contract as the reference (:55-70): returns the cached .pth, downloading it if absent."""
+    if model_name not in MODELS:
+        raise ValueError(f"Unknown model: {model_name}")
+    weights_path = get_model_dir() / f"{model_name}.pth"
+    if not weights_path.exists():
+        urllib.request.urlretrieve(MODELS[model_name]["url"], weights_path)
+    return weights_path
+
+
+def state_dict_keys(num_block: int):
+    """Official Real-ESRGAN key order == the reference's construction order (:122-136)."""
+    keys = ["conv_first"]
+    for b in range(num_block):
+        for r in (1, 2, 3):
+            for k in range(1, 6):
+                keys.append(f"body.{b}.rdb{r}.conv{k}")
+    keys += ["conv_body", "conv_up1", "conv_up2", "conv_hr", "conv_last"]
+    return keys
+
+
+class RRDBNet(nn.Module):
+    """Parameter container with the reference's state_dict layout (:110-138).
+
+    ``load_state_dict(strict=True)`` accepts the official ``params_ema`` / ``params`` dictionaries.
+    The arithmetic of ``forward`` lives in libwowsr.so and is reached through ``RealESRGAN``.
+    """
+
+    def __init__(self, num_in_ch=3, num_out_ch=3, num_feat=64, num_block=23, num_grow_ch=32, scale=4):
+        super().__init__()
+        if (num_in_ch, num_out_ch, num_feat, num_grow_ch, scale) != (3, 3, 64, 32, 4):
+            raise ValueError("the B200 build supports the x4 RRDBNet family only (3->3, nf=64, gc=32)")
+        self.scale = scale
+        self.num_block = num_block
+        self._names = state_dict_keys(num_block)
+        # same creation order as the reference => same default-init RNG stream under manual_seed
+        for name in self._names:
+            cin, cout = self._shape(name, num_feat, num_grow_ch, num_in_ch, num_out_ch)
+            conv = nn.Conv2d(cin, cout, 3, 1, 1)
+            self.register_parameter(name.replace(".", "__") + "__weight", conv.weight)
+            self.register_parameter(name.replace(".", "__") + "__bias", conv.bias)
+
+    @staticmethod
+    def _shape(name, nf, gc, cin0, cout0):
+        if name == "conv_first":
+            return cin0, nf
+        if name == "conv_last":
+            return nf, cout0
+        if name.startswith("body."):
+            k = int(name[-1])
+            return nf + (k - 1) * gc, gc if k < 5 else nf
+        return nf, nf
+
+    # official key names <-> registered parameter names
+    def state_dict(self, *a, **kw):
+        return OrderedDict((n + s, getattr(self, n.replace(".", "__") + "__" + s[1:]).detach())
+                           for n in self._names for s in (".weight", ".bias"))
+
+    def load_state_dict(self, state_dict, strict=True):
+        want = [n + s for n in self._names for s in (".weight", ".bias")]
+        missing = [k for k in want if k not in state_dict]
+        extra = [k for k in state_dict if k not in want]
+        if strict and (missing or extra):
+            raise RuntimeError(f"Error(s) in loading state_dict for RRDBNet: missing {missing[:4]} unexpected {extra[:4]}")
+        with torch.no_grad():
+            for k in want:
+                if k in state_dict:
+                    n, s = k.rsplit(".", 1)
+                    p = getattr(self, n.replace(".", "__") + "__" + s)
+                    v = torch.as_tensor(state_dict[k])
+                    if v.shape != p.shape:
+                        raise RuntimeError(f"size mismatch for {k}: {tuple(v.shape)} vs {tuple(p.shape)}")
+                    p.copy_(v)
+        return self
+
+    def tensors(self):
+        sd = self.state_dict()
+        return [sd[n + s].cpu().numpy() for n in self._names for s in (".weight", ".bias")]
+
+    def forward(self, x):
+        raise NotImplementedError("run the network through RealESRGAN.enhance(); the kernels take uint8 windows")
+
+
+class RealESRGAN:
+    """Real-ESRGAN inference wrapper with the reference's constructor and ``enhance`` (:161-234).
+
+    Extra keyword-only arguments (all optional): ``state_dict`` to supply weights directly (the
+    build box has no network for ``download_weights``), ``precision`` ("bf16" | "fp16") for the
+    tensor-core operand type, ``handle`` to share a libwowsr handle.
+    """
+
+    def __init__(self, scale: int = 4, device: str = None, tile_size: int = 256, model_name: str = None, *,
+                 state_dict=None, precision: str = "bf16", handle=None):
+        self.tile_size = tile_size
+        self.tile_pad = 10
+        if device is None:
+            self.device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        else:
+            self.device = torch.device(device)
+        if model_name is None:
+            model_name = f"realesrgan_x{scale}"
+        if model_name not in MODELS:
+            raise ValueError(f"Unknown model: {model_name}. Available: {list(MODELS.keys())}")
+        if self.device.type != "cuda":
+            raise RuntimeError("this build runs on a B200 only (no CPU fallback); got device=%s" % self.device)
+        config = MODELS[model_name]
+        self.scale = config["scale"]
+        self.model_name = model_name
+        self.precision = precision
+        self.model = RRDBNet(3, 3, config["channels"], config["blocks"], 32, self.scale)
+        if state_dict is None:
+            weights_path = download_weights(model_name)
+            state_dict = torch.load(weights_path, map_location="cpu")
+        if "params_ema" in state_dict:
+            state_dict = state_dict["params_ema"]
+        elif "params" in state_dict:
+            state_dict = state_dict["params"]
+        self.model.load_state_dict(state_dict, strict=True)
+        self.model.eval()
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self._h = handle if handle is not None else _lib.Handle(dev_index)
+        self._h.load_rrdbnet(self.model.tensors(), config["blocks"], config["channels"], 32, precision)
+
+    @torch.no_grad()
+    def enhance(self, img: np.ndarray, outscale: int = 4) -> np.ndarray:
+        """``img`` HxWx3 uint8 (channel order as given) -> 4Hx4Wx3 uint8, synchronous (:217-234)."""
+        if outscale != self.scale:
+            raise ValueError(f"outscale={outscale} is not supported by {self.model_name} (x{self.scale})")
+        if img.ndim != 3 or img.shape[2] != 3:
+            raise ValueError("expected an HxWx3 image")
+        return self._h.enhance_host(np.asarray(img).astype(np.uint8, copy=False), self.tile_size)
+
+    @torch.no_grad()
+    def enhance_float(self, img: np.ndarray):
+        """(uint8 output, float32 pre-quantisation output) — used by the parity tests."""
+        return self._h.enhance_host(np.asarray(img).astype(np.uint8, copy=False), self.tile_size, want_float=True)
+
+    @torch.no_grad()
+    def enhance_cuda(self, img: torch.Tensor) -> torch.Tensor:
+        """Device-resident variant: uint8 HxWx3 CUDA tensor in, uint8 4Hx4Wx3 CUDA tensor out."""
+        assert img.is_cuda and img.dtype == torch.uint8 and img.is_contiguous()
+        H, W = img.shape[:2]
+        out = torch.empty((4 * H, 4 * W, 3), dtype=torch.uint8, device=img.device)
+        self._h.enhance_dev(img.data_ptr(), H, W, self.tile_size, out.data_ptr(),
+                            stream=torch.cuda.current_stream(img.device).cuda_stream)
+        return out
+
+    def _tile_process(self, img):  # kept for interface parity; the planner + stitching are native
+        raise NotImplementedError("tiling runs inside libwowsr (wowsr_plan_windows / wowsr_rrdbnet_forward_windows)")

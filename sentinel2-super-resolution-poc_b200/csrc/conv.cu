@@ -1,0 +1,531 @@
+// Host side of the RRDBNet / EDSR path: weight repacking, TMA tensor maps, per-layer launch
+// plans, window batching, and the enhance()/upsample() entry points of the C ABI.
+//
+// Replaces RRDBNet.forward (cnn_super_resolution.py:140-158) and RealESRGAN.enhance/_tile_process
+// (cnn_super_resolution.py:217-280).  See conv_kernels.cuh for the kernels.
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+
+#include "common.h"
+#include "conv_kernels.cuh"
+
+namespace {
+
+constexpr size_t SMEM_LIMIT = 232448;  // 227 KB opt-in maximum per block on sm_100
+constexpr size_t SMEM_SLACK = 1024 + 1024;  // alignment slack + control block
+
+struct LayerW {
+  int cin = 0, cout = 0, N = 0, n_chunks = 0;
+  size_t chunk_bytes = 0;
+  uint8_t* wpack = nullptr;
+  float* wsimple = nullptr;
+  float* bias = nullptr;
+};
+
+}  // namespace
+
+struct ConvNet {
+  int kind = 0;  // 0 RRDBNet, 1 EDSR
+  int num_block = 0, nf = 64, gc = 32;
+  bool fp16 = false;
+  float res_scale = 1.0f;
+  float* first_w = nullptr;  // [ky][kx][ci][64] fp32
+  float* first_b = nullptr;
+  std::vector<LayerW> layers;
+  DevBuf dense0, dense1, feat, trunk, rrdb, up1, hra, hrb, wins, winxy, err;
+};
+
+void wowsr_net_free(ConvNet* n) {
+  if (!n) return;
+  for (auto& l : n->layers) {
+    if (l.wpack) cudaFree(l.wpack);
+    if (l.wsimple) cudaFree(l.wsimple);
+    if (l.bias) cudaFree(l.bias);
+  }
+  if (n->first_w) cudaFree(n->first_w);
+  if (n->first_b) cudaFree(n->first_b);
+  DevBuf* bufs[] = {&n->dense0, &n->dense1, &n->feat, &n->trunk, &n->rrdb, &n->up1, &n->hra, &n->hrb, &n->wins, &n->winxy, &n->err};
+  for (DevBuf* b : bufs)
+    if (b->p) cudaFree(b->p);
+  delete n;
+}
+
+namespace {
+
+inline uint16_t to_t(float v, bool fp16) {
+  if (fp16) {
+    __half h = __float2half_rn(v);
+    return *reinterpret_cast<uint16_t*>(&h);
+  }
+  __nv_bfloat16 b = __float2bfloat16_rn(v);
+  return *reinterpret_cast<uint16_t*>(&b);
+}
+inline float from_t(uint16_t u, bool fp16) {
+  if (fp16) return __half2float(*reinterpret_cast<__half*>(&u));
+  return __bfloat162float(*reinterpret_cast<__nv_bfloat16*>(&u));
+}
+
+int pad_n(int cout) { return cout <= 16 ? 16 : (cout <= 32 ? 32 : 64); }
+
+// weight OIHW fp32 -> (a) smem image for the tensor-core kernel, (b) [ky][kx][ci][N] for the simple one
+int upload_layer(wowsr_ctx* ctx, LayerW& L, const float* w, const float* b, int cin, int cout, bool fp16) {
+  if (cin % 16 != 0 || cout > 64 || cout < 1) return wowsr_fail(ctx, WOWSR_ERR_UNSUPPORTED, "conv %d->%d unsupported", cin, cout);
+  L.cin = cin;
+  L.cout = cout;
+  L.N = pad_n(cout);
+  L.n_chunks = (cin + 63) / 64;
+  const int N = L.N;
+  L.chunk_bytes = (size_t)3 * 3 * N * 128;
+  std::vector<uint8_t> pack(L.chunk_bytes * L.n_chunks, 0);
+  std::vector<float> simple((size_t)9 * cin * N, 0.0f);
+  for (int c = 0; c < L.n_chunks; c++)
+    for (int kx = 0; kx < 3; kx++)
+      for (int j = 0; j < 3; j++) {
+        const int ky = 2 - j;
+        for (int co = 0; co < cout; co++) {
+          const int row = j * N + co;
+          for (int ch = 0; ch < 64; ch++) {
+            const int ci = c * 64 + ch;
+            if (ci >= cin) break;
+            const float v = w[(((size_t)co * cin + ci) * 3 + ky) * 3 + kx];
+            const uint16_t t = to_t(v, fp16);
+            size_t off = (size_t)c * L.chunk_bytes + (size_t)kx * (3 * N * 128) + (size_t)row * 128 +
+                         (size_t)(((ch >> 3) ^ (row & 7)) << 4) + (size_t)(ch & 7) * 2;
+            memcpy(&pack[off], &t, 2);
+          }
+        }
+      }
+  for (int ky = 0; ky < 3; ky++)
+    for (int kx = 0; kx < 3; kx++)
+      for (int ci = 0; ci < cin; ci++)
+        for (int co = 0; co < cout; co++)
+          simple[((size_t)(ky * 3 + kx) * cin + ci) * N + co] =
+              from_t(to_t(w[(((size_t)co * cin + ci) * 3 + ky) * 3 + kx], fp16), fp16);
+  std::vector<float> bias(64, 0.0f);
+  for (int co = 0; co < cout; co++) bias[co] = b ? b[co] : 0.0f;
+  WCUDA(ctx, cudaMalloc((void**)&L.wpack, pack.size()));
+  WCUDA(ctx, cudaMalloc((void**)&L.wsimple, simple.size() * 4));
+  WCUDA(ctx, cudaMalloc((void**)&L.bias, 64 * 4));
+  WCUDA(ctx, cudaMemcpy(L.wpack, pack.data(), pack.size(), cudaMemcpyHostToDevice));
+  WCUDA(ctx, cudaMemcpy(L.wsimple, simple.data(), simple.size() * 4, cudaMemcpyHostToDevice));
+  WCUDA(ctx, cudaMemcpy(L.bias, bias.data(), 64 * 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int upload_first(wowsr_ctx* ctx, ConvNet* net, const float* w, const float* b, int cin, int cout) {
+  if (cin != 3 || cout != 64) return wowsr_fail(ctx, WOWSR_ERR_UNSUPPORTED, "first conv must be 3->64 (got %d->%d)", cin, cout);
+  std::vector<float> ww(27 * 64);
+  for (int ky = 0; ky < 3; ky++)
+    for (int kx = 0; kx < 3; kx++)
+      for (int ci = 0; ci < 3; ci++)
+        for (int co = 0; co < 64; co++) ww[((ky * 3 + kx) * 3 + ci) * 64 + co] = w[(((size_t)co * 3 + ci) * 3 + ky) * 3 + kx];
+  WCUDA(ctx, cudaMalloc((void**)&net->first_w, ww.size() * 4));
+  WCUDA(ctx, cudaMalloc((void**)&net->first_b, 64 * 4));
+  WCUDA(ctx, cudaMemcpy(net->first_w, ww.data(), ww.size() * 4, cudaMemcpyHostToDevice));
+  WCUDA(ctx, cudaMemcpy(net->first_b, b, 64 * 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
+  }
+  return fn;
+}
+
+// 4-D map over an NHWC activation buffer: dims (C, W, H, N), box (64 ch, 130 px, 1 row, 1 window)
+int make_tmap(wowsr_ctx* ctx, CUtensorMap* m, const void* base, int C, int W, int H, int Nw, bool fp16) {
+  auto enc = get_encode();
+  if (!enc) return wowsr_fail(ctx, WOWSR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Nw};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * W, (cuuint64_t)C * 2 * W * H};
+  cuuint32_t box[4] = {64, (cuuint32_t)TC_AROWS, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base),
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return wowsr_fail(ctx, WOWSR_ERR_CUDA, "cuTensorMapEncodeTiled(C=%d,W=%d,H=%d,N=%d) -> CUresult %d", C, W, H, Nw, (int)r);
+  return 0;
+}
+
+struct LayerIO {
+  const void* in = nullptr;  // activation buffer (T), C_total channels per pixel
+  int in_C = 0;
+  int Nw = 0, h = 0, w = 0;
+  int act = 0;
+  float scale1 = 1.0f, scale2 = 1.0f;
+  const float* res1 = nullptr;
+  const float* res2 = nullptr;
+  float* out_f32_a = nullptr;
+  float* out_f32_b = nullptr;
+  void* out_t = nullptr;
+  int out_stride = 0, out_choff = 0, out_rep = 1;
+  int final = 0;
+  uint8_t* out_u8 = nullptr;
+  long long out_u8_pitch = 0;
+  float* out_img_f32 = nullptr;
+  long long out_img_f32_pitch = 0;
+  const WinDev* wins = nullptr;
+};
+
+int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, cudaStream_t st) {
+  ConvParams P;
+  memset(&P, 0, sizeof P);
+  P.Nw = io.Nw; P.h = io.h; P.w = io.w;
+  P.cin = L.cin; P.n_chunks = L.n_chunks; P.N = L.N; P.cout = L.cout;
+  const int N = L.N;
+  int R = 256 / N;
+  if (R > 8) R = 8;
+  int64_t optR = wowsr_opt(ctx, "tc_rows", 0);
+  if (optR > 0 && optR * N <= 256) R = (int)optR;
+  P.R = R;
+  P.tiles_x = (io.w + TC_RUN - 1) / TC_RUN;
+  P.tiles_y = (io.h + R - 1) / R;
+  P.n_tiles = P.tiles_x * P.tiles_y * io.Nw;
+  P.flags = (int)wowsr_opt(ctx, "tc_flags", CF_STACK) | (net->fp16 ? CF_FP16 : 0);
+  P.idesc_base = make_idesc_f16(128, 0, net->fp16);
+  P.w_chunk_bytes = (uint32_t)L.chunk_bytes;
+  size_t wtotal = L.chunk_bytes * L.n_chunks;
+  if (wtotal + 4 * (size_t)TC_ASTAGE + SMEM_SLACK <= SMEM_LIMIT && L.n_chunks <= TC_MAX_WBUF &&
+      !wowsr_opt(ctx, "tc_force_stream", 0)) {
+    P.w_resident = 1;
+    P.n_wbuf = L.n_chunks;
+  } else {
+    P.w_resident = 0;
+    P.n_wbuf = 2;
+  }
+  size_t left = SMEM_LIMIT - SMEM_SLACK - (size_t)P.n_wbuf * L.chunk_bytes;
+  int stages = (int)(left / TC_ASTAGE);
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  int64_t optS = wowsr_opt(ctx, "tc_stages", 0);
+  if (optS > 0 && optS < stages) stages = (int)optS;
+  if (stages < 2) return wowsr_fail(ctx, WOWSR_ERR_UNSUPPORTED, "not enough shared memory for conv %d->%d", L.cin, L.cout);
+  P.n_stage = stages;
+  P.wpack = L.wpack; P.wsimple = L.wsimple; P.bias = L.bias;
+  P.in = io.in; P.in_stride = io.in_C;
+  P.act = io.act; P.scale1 = io.scale1; P.res1 = io.res1; P.scale2 = io.scale2; P.res2 = io.res2;
+  P.out_f32_a = io.out_f32_a; P.out_f32_b = io.out_f32_b;
+  P.out_t = io.out_t; P.out_stride = io.out_stride; P.out_choff = io.out_choff; P.out_rep = io.out_rep;
+  P.final = io.final; P.out_u8 = io.out_u8; P.out_u8_pitch = io.out_u8_pitch;
+  P.out_img_f32 = io.out_img_f32; P.out_img_f32_pitch = io.out_img_f32_pitch; P.wins = io.wins;
+  P.err_flag = (int*)net->err.p;
+
+  if (wowsr_opt(ctx, "conv_impl", 0) == 1) {
+    long long total = (long long)io.Nw * io.h * io.w;
+    unsigned blocks = (unsigned)((total + 127) / 128);
+#define SIMPLE(NN)                                                                              \
+  if (net->fp16) conv3x3_simple_kernel<NN, true><<<blocks, 128, 0, st>>>(P);                    \
+  else conv3x3_simple_kernel<NN, false><<<blocks, 128, 0, st>>>(P);
+    if (N == 16) { SIMPLE(16) } else if (N == 32) { SIMPLE(32) } else { SIMPLE(64) }
+#undef SIMPLE
+    WLAUNCH_CHECK(ctx);
+    return 0;
+  }
+  CUtensorMap tmap;
+  if (int e = make_tmap(ctx, &tmap, io.in, io.in_C, io.w, io.h, io.Nw, net->fp16)) return e;
+  size_t smem = (size_t)P.n_stage * TC_ASTAGE + (size_t)P.n_wbuf * L.chunk_bytes + SMEM_SLACK;
+  int grid = P.n_tiles < ctx->sm_count ? P.n_tiles : ctx->sm_count;
+  int64_t optG = wowsr_opt(ctx, "tc_grid", 0);
+  if (optG > 0 && optG < grid) grid = (int)optG;
+  if (net->fp16) {
+    WCUDA(ctx, cudaFuncSetAttribute(conv3x3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+    conv3x3_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(tmap, P);
+  } else {
+    WCUDA(ctx, cudaFuncSetAttribute(conv3x3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+    conv3x3_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(tmap, P);
+  }
+  WLAUNCH_CHECK(ctx);
+  return 0;
+}
+
+int check_err_flag(wowsr_ctx* ctx, ConvNet* net, cudaStream_t st) {
+  int flag = 0;
+  WCUDA(ctx, cudaMemcpyAsync(&flag, net->err.p, 4, cudaMemcpyDeviceToHost, st));
+  WCUDA(ctx, cudaStreamSynchronize(st));
+  if (flag) {
+    cudaMemsetAsync(net->err.p, 0, 4, st);
+    return wowsr_fail(ctx, WOWSR_ERR_CUDA, "tensor-core conv kernel watchdog tripped (code %d)", flag);
+  }
+  return 0;
+}
+
+// One batch of equally sized windows through the whole RRDBNet.
+int rrdbnet_batch(wowsr_ctx* ctx, ConvNet* net, const uint8_t* img, long long pitch, const wowsr_window* wins, int nb,
+                  uint8_t* out, long long out_pitch, float* out_f32, long long out_f32_pitch, cudaStream_t st) {
+  const int h = wins[0].y1 - wins[0].y0, w = wins[0].x1 - wins[0].x0;
+  const size_t px = (size_t)nb * h * w;
+  const bool fp16 = net->fp16;
+  if (int e = wowsr_ensure(ctx, net->dense0, px * 192 * 2)) return e;
+  if (int e = wowsr_ensure(ctx, net->dense1, px * 192 * 2)) return e;
+  if (int e = wowsr_ensure(ctx, net->feat, px * 64 * 4)) return e;
+  if (int e = wowsr_ensure(ctx, net->trunk, px * 64 * 4)) return e;
+  if (int e = wowsr_ensure(ctx, net->rrdb, px * 64 * 4)) return e;
+  if (int e = wowsr_ensure(ctx, net->up1, px * 4 * 64 * 2)) return e;
+  if (int e = wowsr_ensure(ctx, net->hra, px * 16 * 64 * 2)) return e;
+  if (int e = wowsr_ensure(ctx, net->hrb, px * 16 * 64 * 2)) return e;
+  if (int e = wowsr_ensure(ctx, net->wins, (size_t)nb * sizeof(WinDev))) return e;
+  if (int e = wowsr_ensure(ctx, net->winxy, (size_t)nb * 8)) return e;
+  std::vector<WinDev> wd(nb);
+  std::vector<int> wxy(2 * nb);
+  for (int i = 0; i < nb; i++) {
+    wd[i] = WinDev{4 * wins[i].x0, 4 * wins[i].y0, 4 * wins[i].ox0, 4 * wins[i].oy0, 4 * wins[i].ox1, 4 * wins[i].oy1};
+    wxy[2 * i] = wins[i].x0;
+    wxy[2 * i + 1] = wins[i].y0;
+  }
+  WCUDA(ctx, cudaMemcpyAsync(net->wins.p, wd.data(), nb * sizeof(WinDev), cudaMemcpyHostToDevice, st));
+  WCUDA(ctx, cudaMemcpyAsync(net->winxy.p, wxy.data(), nb * 8, cudaMemcpyHostToDevice, st));
+  WCUDA(ctx, cudaStreamSynchronize(st));  // host vectors go out of scope
+
+  WCUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+  {
+    FirstParams F;
+    memset(&F, 0, sizeof F);
+    F.img = img; F.pitch = pitch; F.cin = 3; F.win_xy = (const int*)net->winxy.p;
+    F.Nw = nb; F.h = h; F.w = w; F.weight = net->first_w; F.bias = net->first_b;
+    F.f32_a = (float*)net->feat.p; F.f32_b = (float*)net->trunk.p; F.f32_c = (float*)net->rrdb.p;
+    F.out_t = net->dense0.p; F.out_stride = 192; F.in_scale_div = 255.0f;
+    dim3 grid((unsigned)((px + 127) / 128), 4);
+    if (fp16) conv_first_kernel<true><<<grid, 128, 0, st>>>(F);
+    else conv_first_kernel<false><<<grid, 128, 0, st>>>(F);
+    WLAUNCH_CHECK(ctx);
+  }
+  WCUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+  void* cur = net->dense0.p;
+  void* nxt = net->dense1.p;
+  size_t li = 0;
+  for (int b = 0; b < net->num_block; b++)
+    for (int r = 0; r < 3; r++) {
+      for (int k = 0; k < 4; k++) {
+        LayerIO io;
+        io.in = cur; io.in_C = 192; io.Nw = nb; io.h = h; io.w = w;
+        io.act = 1;
+        io.out_t = cur; io.out_stride = 192; io.out_choff = 64 + 32 * k;
+        if (int e = run_conv(ctx, net, net->layers[li++], io, st)) return e;
+      }
+      LayerIO io;
+      io.in = cur; io.in_C = 192; io.Nw = nb; io.h = h; io.w = w;
+      io.scale1 = 0.2f; io.res1 = (const float*)net->trunk.p;
+      io.out_f32_a = (float*)net->trunk.p;
+      if (r == 2) {
+        io.scale2 = 0.2f; io.res2 = (const float*)net->rrdb.p;
+        io.out_f32_b = (float*)net->rrdb.p;
+      }
+      io.out_t = nxt; io.out_stride = 192; io.out_choff = 0;
+      if (int e = run_conv(ctx, net, net->layers[li++], io, st)) return e;
+      std::swap(cur, nxt);
+    }
+  WCUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+  {  // conv_body + long skip, written nearest-x2 replicated for conv_up1
+    LayerIO io;
+    io.in = cur; io.in_C = 192; io.Nw = nb; io.h = h; io.w = w;
+    io.scale1 = 1.0f; io.res1 = (const float*)net->feat.p;
+    io.out_t = net->up1.p; io.out_stride = 64; io.out_rep = 2;
+    if (int e = run_conv(ctx, net, net->layers[li++], io, st)) return e;
+  }
+  {  // conv_up1 @2x + lrelu, replicated for conv_up2
+    LayerIO io;
+    io.in = net->up1.p; io.in_C = 64; io.Nw = nb; io.h = 2 * h; io.w = 2 * w;
+    io.act = 1; io.out_t = net->hra.p; io.out_stride = 64; io.out_rep = 2;
+    if (int e = run_conv(ctx, net, net->layers[li++], io, st)) return e;
+  }
+  {  // conv_up2 @4x + lrelu
+    LayerIO io;
+    io.in = net->hra.p; io.in_C = 64; io.Nw = nb; io.h = 4 * h; io.w = 4 * w;
+    io.act = 1; io.out_t = net->hrb.p; io.out_stride = 64;
+    if (int e = run_conv(ctx, net, net->layers[li++], io, st)) return e;
+  }
+  {  // conv_hr + lrelu
+    LayerIO io;
+    io.in = net->hrb.p; io.in_C = 64; io.Nw = nb; io.h = 4 * h; io.w = 4 * w;
+    io.act = 1; io.out_t = net->hra.p; io.out_stride = 64;
+    if (int e = run_conv(ctx, net, net->layers[li++], io, st)) return e;
+  }
+  {  // conv_last + quantise + stitch
+    LayerIO io;
+    io.in = net->hra.p; io.in_C = 64; io.Nw = nb; io.h = 4 * h; io.w = 4 * w;
+    io.final = 1; io.out_u8 = out; io.out_u8_pitch = out_pitch;
+    io.out_img_f32 = out_f32; io.out_img_f32_pitch = out_f32_pitch / 4;
+    io.wins = (const WinDev*)net->wins.p;
+    if (int e = run_conv(ctx, net, net->layers[li++], io, st)) return e;
+  }
+  WCUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+  return 0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+
+extern "C" int wowsr_load_rrdbnet(wowsr_ctx* ctx, int32_t num_block, int32_t num_feat, int32_t num_grow,
+                                  const float* const* tensors, int32_t n_tensors, int32_t precision) {
+  if (!ctx || !tensors) return WOWSR_ERR_ARG;
+  if (num_feat != 64 || num_grow != 32)
+    return wowsr_fail(ctx, WOWSR_ERR_UNSUPPORTED, "only num_feat=64, num_grow=32 (x4plus / anime-6B) are built");
+  const int n_convs = 1 + num_block * 15 + 5;
+  if (n_tensors != 2 * n_convs) return wowsr_fail(ctx, WOWSR_ERR_ARG, "expected %d tensors, got %d", 2 * n_convs, n_tensors);
+  DeviceGuard g(ctx->device);
+  wowsr_net_free(ctx->net);
+  ctx->net = nullptr;
+  ConvNet* net = new ConvNet();
+  net->kind = 0;
+  net->num_block = num_block;
+  net->fp16 = precision == WOWSR_PREC_FP16;
+  int t = 0;
+  int e = upload_first(ctx, net, tensors[0], tensors[1], 3, 64);
+  t = 2;
+  for (int b = 0; b < num_block && !e; b++)
+    for (int r = 0; r < 3 && !e; r++)
+      for (int k = 0; k < 5 && !e; k++) {
+        net->layers.emplace_back();
+        e = upload_layer(ctx, net->layers.back(), tensors[t], tensors[t + 1], 64 + 32 * k, k < 4 ? 32 : 64, net->fp16);
+        t += 2;
+      }
+  for (int i = 0; i < 5 && !e; i++) {  // conv_body, conv_up1, conv_up2, conv_hr, conv_last
+    net->layers.emplace_back();
+    e = upload_layer(ctx, net->layers.back(), tensors[t], tensors[t + 1], 64, i < 4 ? 64 : 3, net->fp16);
+    t += 2;
+  }
+  if (!e) e = wowsr_ensure(ctx, net->err, 4);
+  if (!e && cudaMemset(net->err.p, 0, 4) != cudaSuccess) e = wowsr_fail(ctx, WOWSR_ERR_CUDA, "memset");
+  if (e) {
+    wowsr_net_free(net);
+    return e;
+  }
+  ctx->net = net;
+  return WOWSR_OK;
+}
+
+extern "C" int wowsr_rrdbnet_forward_windows(wowsr_ctx* ctx, const uint8_t* img_dev, int32_t H, int32_t W, int64_t pitch,
+                                             const wowsr_window* windows, int32_t n, uint8_t* out_dev, int64_t out_pitch,
+                                             float* out_f32, int64_t out_f32_pitch, void* stream) {
+  if (!ctx || !img_dev || !windows || n < 1 || !out_dev) return WOWSR_ERR_ARG;
+  if (!ctx->net || ctx->net->kind != 0) return wowsr_fail(ctx, WOWSR_ERR_STATE, "wowsr_load_rrdbnet has not been called");
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int h = windows[0].y1 - windows[0].y0, w = windows[0].x1 - windows[0].x0;
+  for (int i = 0; i < n; i++) {
+    const wowsr_window& q = windows[i];
+    if (q.y1 - q.y0 != h || q.x1 - q.x0 != w || q.x0 < 0 || q.y0 < 0 || q.x1 > W || q.y1 > H)
+      return wowsr_fail(ctx, WOWSR_ERR_ARG, "window %d has a different size or lies outside the image", i);
+  }
+  // batch size from the workspace budget: 6144 B per LR pixel (data layout)
+  int64_t budget = wowsr_opt(ctx, "mem_budget_mb", 49152) << 20;
+  int64_t per_win = (int64_t)h * w * 6144;
+  int maxb = (int)std::max<int64_t>(1, budget / per_win);
+  int nbatches = (n + maxb - 1) / maxb;
+  int per = (n + nbatches - 1) / nbatches;
+  float t_head = 0, t_trunk = 0, t_tail = 0;
+  for (int i0 = 0; i0 < n; i0 += per) {
+    int nb = std::min(per, n - i0);
+    if (int e = rrdbnet_batch(ctx, ctx->net, img_dev, pitch, windows + i0, nb, out_dev, out_pitch, out_f32, out_f32_pitch, st))
+      return e;
+    if (int e = check_err_flag(ctx, ctx->net, st)) return e;
+    float a = 0, b = 0, c = 0;
+    cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&c, ctx->ev[2], ctx->ev[3]);
+    t_head += a; t_trunk += b; t_tail += c;
+  }
+  ctx->timing[0] = t_head + t_trunk + t_tail;
+  ctx->timing[1] = t_head; ctx->timing[2] = t_trunk; ctx->timing[3] = t_tail;
+  return WOWSR_OK;
+}
+
+extern "C" int wowsr_enhance_dev(wowsr_ctx* ctx, const uint8_t* img_dev, int32_t H, int32_t W, int32_t tile_size,
+                                 uint8_t* out_dev, float* out_f32_dev, void* stream) {
+  if (!ctx || H < 1 || W < 1 || tile_size < 1) return WOWSR_ERR_ARG;
+  int n = wowsr_plan_windows(H, W, tile_size, 10, nullptr, 0);
+  if (n < 1) return wowsr_fail(ctx, WOWSR_ERR_ARG, "planner failed");
+  std::vector<wowsr_window> wins(n);
+  wowsr_plan_windows(H, W, tile_size, 10, wins.data(), n);
+  return wowsr_rrdbnet_forward_windows(ctx, img_dev, H, W, (int64_t)W * 3, wins.data(), n, out_dev, (int64_t)W * 4 * 3,
+                                       out_f32_dev, (int64_t)W * 4 * 3 * 4, stream);
+}
+
+extern "C" int wowsr_enhance_host(wowsr_ctx* ctx, const uint8_t* img_host, int32_t H, int32_t W, int32_t tile_size,
+                                  uint8_t* out_host, float* out_f32_host) {
+  if (!ctx || !img_host || !out_host) return WOWSR_ERR_ARG;
+  DeviceGuard g(ctx->device);
+  size_t in_bytes = (size_t)H * W * 3, out_bytes = in_bytes * 16;
+  if (int e = wowsr_ensure(ctx, ctx->img_in, in_bytes)) return e;
+  if (int e = wowsr_ensure(ctx, ctx->img_out, out_bytes)) return e;
+  if (out_f32_host)
+    if (int e = wowsr_ensure(ctx, ctx->img_out_f32, out_bytes * 4)) return e;
+  WCUDA(ctx, cudaMemcpyAsync(ctx->img_in.p, img_host, in_bytes, cudaMemcpyHostToDevice, 0));
+  if (int e = wowsr_enhance_dev(ctx, (const uint8_t*)ctx->img_in.p, H, W, tile_size, (uint8_t*)ctx->img_out.p,
+                                out_f32_host ? (float*)ctx->img_out_f32.p : nullptr, nullptr))
+    return e;
+  WCUDA(ctx, cudaMemcpyAsync(out_host, ctx->img_out.p, out_bytes, cudaMemcpyDeviceToHost, 0));
+  if (out_f32_host) WCUDA(ctx, cudaMemcpyAsync(out_f32_host, ctx->img_out_f32.p, out_bytes * 4, cudaMemcpyDeviceToHost, 0));
+  WCUDA(ctx, cudaStreamSynchronize(0));
+  return WOWSR_OK;
+}
+
+extern "C" int32_t wowsr_get_timing(const wowsr_ctx* ctx, float* ms, int32_t cap) {
+  if (!ctx || !ms) return WOWSR_ERR_ARG;
+  int n = cap < 4 ? cap : 4;
+  for (int i = 0; i < n; i++) ms[i] = ctx->timing[i];
+  return n;
+}
+
+extern "C" int wowsr_conv3x3_host(wowsr_ctx* ctx, const float* in, int32_t n, int32_t h, int32_t w, int32_t cin,
+                                  const float* weight, const float* bias, int32_t cout, int32_t act, int32_t precision,
+                                  float* out) {
+  if (!ctx || !in || !weight || !out || n < 1 || h < 1 || w < 1) return WOWSR_ERR_ARG;
+  DeviceGuard g(ctx->device);
+  const bool fp16 = precision == WOWSR_PREC_FP16;
+  ConvNet* net = new ConvNet();
+  net->fp16 = fp16;
+  net->layers.emplace_back();
+  int e = upload_layer(ctx, net->layers[0], weight, bias, cin, cout, fp16);
+  const size_t px = (size_t)n * h * w;
+  const int C = (cin + 63) / 64 * 64;
+  DevBuf din, dout;
+  if (!e) e = wowsr_ensure(ctx, din, px * C * 2);
+  if (!e) e = wowsr_ensure(ctx, dout, px * 64 * 4);
+  if (!e) e = wowsr_ensure(ctx, net->err, 4);
+  if (!e) {
+    std::vector<uint16_t> t(px * C, 0);
+    for (size_t p = 0; p < px; p++)
+      for (int c = 0; c < cin; c++) t[p * C + c] = to_t(in[p * cin + c], fp16);
+    cudaError_t ce = cudaMemcpy(din.p, t.data(), t.size() * 2, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaMemset(dout.p, 0, px * 64 * 4);
+    if (ce == cudaSuccess) ce = cudaMemset(net->err.p, 0, 4);
+    if (ce != cudaSuccess) e = wowsr_fail(ctx, WOWSR_ERR_CUDA, "conv3x3_host upload: %s", cudaGetErrorString(ce));
+  }
+  if (!e) {
+    LayerIO io;
+    io.in = din.p; io.in_C = C; io.Nw = n; io.h = h; io.w = w; io.act = act;
+    io.out_f32_a = (float*)dout.p;
+    e = run_conv(ctx, net, net->layers[0], io, 0);
+  }
+  if (!e) e = check_err_flag(ctx, net, 0);
+  if (!e) {
+    std::vector<float> o(px * 64);
+    cudaError_t ce = cudaMemcpy(o.data(), dout.p, o.size() * 4, cudaMemcpyDeviceToHost);
+    if (ce != cudaSuccess) e = wowsr_fail(ctx, WOWSR_ERR_CUDA, "conv3x3_host download: %s", cudaGetErrorString(ce));
+    else
+      for (size_t p = 0; p < px; p++)
+        for (int c = 0; c < cout; c++) out[p * cout + c] = o[p * 64 + c];
+  }
+  if (din.p) cudaFree(din.p);
+  if (dout.p) cudaFree(dout.p);
+  wowsr_net_free(net);
+  return e;
+}
+
+extern "C" int wowsr_load_edsr(wowsr_ctx* ctx, int32_t, int32_t, float, const float* const*, int32_t, int32_t) {
+  return wowsr_fail(ctx, WOWSR_ERR_UNSUPPORTED, "EDSR path not built yet");
+}
+extern "C" int wowsr_edsr_upsample_host(wowsr_ctx* ctx, const uint8_t*, int32_t, int32_t, uint8_t*, float*) {
+  return wowsr_fail(ctx, WOWSR_ERR_UNSUPPORTED, "EDSR path not built yet");
+}

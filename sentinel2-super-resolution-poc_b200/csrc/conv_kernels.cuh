@@ -1,0 +1,508 @@
+// 3x3 convolution kernels for the RRDBNet / EDSR hot path (cnn_super_resolution.py:73-158).
+//
+// conv3x3_tc_kernel — the product kernel.  Implicit GEMM on tcgen05 tensor cores:
+//   * M = a run of 128 output pixels along x of one image row; a CTA tile is R such rows.
+//   * K = 9 taps x Cin, consumed in 64-channel chunks; each pipeline stage is ONE input row of the
+//     tile (130 pixels x 64 channels, 128-byte-swizzled) fetched by a 4-D TMA box load from the NHWC
+//     activation buffer.  TMA out-of-bounds zero fill provides the conv zero padding at window
+//     borders (windows are independent, cnn_super_resolution.py:256-257).
+//   * the three horizontal taps reuse the SAME smem row through row-shifted UMMA descriptors
+//     (start address + kx*128 B), so each activation byte is fetched from L2 once per tile row.
+//   * the three vertical taps are stacked along N: one tcgen05.mma with N = 3*Cout multiplies an
+//     input row by [W(ky=2) | W(ky=1) | W(ky=0)] and accumulates into the TMEM column blocks of output
+//     rows y-1, y, y+1, so the A operand is read from smem once for three taps.
+//   * accumulators (R rows x Cout fp32 columns, double buffered) live in TMEM; 4 epilogue warps drain
+//     them with tcgen05.ld and apply the fused epilogue (bias, LeakyReLU, residual scale-add in fp32,
+//     channel-offset store into the dense NHWC buffer — no concat copies — optional nearest-x2
+//     replication for the following upsample conv, or final uint8 quantisation + tile stitching).
+//
+// conv3x3_simple_kernel — a CUDA-core direct convolution with the same operand rounding and the same
+// epilogue; used for bring-up and as the on-device cross-check of the tensor-core kernel in tests.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "ptx.cuh"
+
+constexpr int TC_THREADS = 192;       // warp0 TMA producer, warp1 MMA issuer, warps2-5 epilogue
+constexpr int TC_RUN = 128;           // output pixels per M-run
+constexpr int TC_AROWS = TC_RUN + 2;  // input pixels per row stage
+constexpr int TC_ABYTES = TC_AROWS * 128;
+constexpr int TC_ASTAGE = 17408;      // TC_ABYTES rounded up to 1024
+constexpr int TC_MAX_STAGES = 10;
+constexpr int TC_MAX_WBUF = 4;
+
+constexpr int CF_STACK = 1;    // stack the three ky taps along N
+constexpr int CF_BASEOFF = 2;  // put (start_addr>>7)&7 into the descriptor base-offset field
+constexpr int CF_FP16 = 4;     // fp16 operands instead of bf16
+
+struct WinDev {  // output-resolution window record for the final layer
+  int X0, Y0;              // origin of this window's output in the stitched image
+  int OX0, OY0, OX1, OY1;  // owned rectangle in the stitched image (last-writer-wins resolved)
+};
+
+struct ConvParams {
+  int Nw, h, w;       // windows in the batch, layer resolution
+  int cin, n_chunks;  // input channels (multiple of 16), 64-channel chunks
+  int N, cout;        // padded / real output channels
+  int R, tiles_x, tiles_y, n_tiles;
+  int flags;
+  uint32_t idesc_base;  // instruction descriptor with N = 0
+  int w_resident, n_wbuf, n_stage;
+  uint32_t w_chunk_bytes;
+  const uint8_t* wpack;  // [chunk][kx][j=2-ky][co][64ch] K-major, 128B-swizzled image of smem
+  const float* wsimple;  // [ky][kx][ci][N] operand-rounded weights for the simple kernel
+  const float* bias;     // [N]
+  const void* in;        // simple kernel: input activations (T), pixel stride in_stride, offset 0
+  int in_stride;
+  // epilogue
+  int act;               // LeakyReLU(0.2)
+  float scale1;          // v = v*scale1 + res1
+  const float* res1;     // fp32 [pix][64] or null
+  float scale2;          // v = v*scale2 + res2
+  const float* res2;
+  float* out_f32_a;      // fp32 [pix][64] stores of v (may alias res1/res2: same-pixel RMW)
+  float* out_f32_b;
+  void* out_t;           // T output, pixel stride out_stride (elements), channel offset out_choff
+  int out_stride, out_choff, out_rep;
+  // final layer
+  int final;
+  uint8_t* out_u8;
+  long long out_u8_pitch;
+  float* out_img_f32;
+  long long out_img_f32_pitch;  // in floats
+  const WinDev* wins;
+  int* err_flag;
+};
+
+// ---------------------------------------------------------------------------------------------
+// fused epilogue for NCH consecutive channels [ch0, ch0+NCH) of one output pixel
+// ---------------------------------------------------------------------------------------------
+
+template <int NCH, bool FP16>
+__device__ __forceinline__ void epilogue_pixel(const ConvParams& P, int n, int y, int x, int ch0, float (&v)[NCH],
+                                               const float* __restrict__ bias) {
+#pragma unroll
+  for (int i = 0; i < NCH; i++) v[i] = __fadd_rn(v[i], bias[ch0 + i]);
+  if (P.final) {
+    const WinDev wd = P.wins[n];
+    int X = wd.X0 + x, Y = wd.Y0 + y;
+    if (X >= wd.OX0 && X < wd.OX1 && Y >= wd.OY0 && Y < wd.OY1) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        if (c < P.cout) {
+          float q = fminf(fmaxf(__fmul_rn(v[c], 255.0f), 0.0f), 255.0f);  // (out*255).clip(0,255).astype(u8)
+          P.out_u8[(long long)Y * P.out_u8_pitch + (long long)X * 3 + c] = (uint8_t)(int)q;
+          if (P.out_img_f32) P.out_img_f32[(long long)Y * P.out_img_f32_pitch + (long long)X * 3 + c] = v[c];
+        }
+      }
+    }
+    return;
+  }
+  const long long pix = ((long long)n * P.h + y) * P.w + x;
+  if (P.res1) {
+    const float4* r = reinterpret_cast<const float4*>(P.res1 + pix * 64 + ch0);
+#pragma unroll
+    for (int i = 0; i < NCH / 4; i++) {
+      float4 t = r[i];
+      v[4 * i + 0] = __fadd_rn(__fmul_rn(v[4 * i + 0], P.scale1), t.x);
+      v[4 * i + 1] = __fadd_rn(__fmul_rn(v[4 * i + 1], P.scale1), t.y);
+      v[4 * i + 2] = __fadd_rn(__fmul_rn(v[4 * i + 2], P.scale1), t.z);
+      v[4 * i + 3] = __fadd_rn(__fmul_rn(v[4 * i + 3], P.scale1), t.w);
+    }
+  }
+  if (P.res2) {
+    const float4* r = reinterpret_cast<const float4*>(P.res2 + pix * 64 + ch0);
+#pragma unroll
+    for (int i = 0; i < NCH / 4; i++) {
+      float4 t = r[i];
+      v[4 * i + 0] = __fadd_rn(__fmul_rn(v[4 * i + 0], P.scale2), t.x);
+      v[4 * i + 1] = __fadd_rn(__fmul_rn(v[4 * i + 1], P.scale2), t.y);
+      v[4 * i + 2] = __fadd_rn(__fmul_rn(v[4 * i + 2], P.scale2), t.z);
+      v[4 * i + 3] = __fadd_rn(__fmul_rn(v[4 * i + 3], P.scale2), t.w);
+    }
+  }
+  if (P.act) {
+#pragma unroll
+    for (int i = 0; i < NCH; i++) v[i] = v[i] >= 0.0f ? v[i] : __fmul_rn(v[i], 0.2f);
+  }
+  if (P.out_f32_a) {
+    float4* o = reinterpret_cast<float4*>(P.out_f32_a + pix * 64 + ch0);
+#pragma unroll
+    for (int i = 0; i < NCH / 4; i++) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  }
+  if (P.out_f32_b) {
+    float4* o = reinterpret_cast<float4*>(P.out_f32_b + pix * 64 + ch0);
+#pragma unroll
+    for (int i = 0; i < NCH / 4; i++) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  }
+  if (P.out_t) {
+    uint32_t pk[NCH / 2];
+#pragma unroll
+    for (int i = 0; i < NCH / 2; i++) {
+      if (FP16) {
+        __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        pk[i] = *reinterpret_cast<uint32_t*>(&hh);
+      } else {
+        __nv_bfloat162 bb = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        pk[i] = *reinterpret_cast<uint32_t*>(&bb);
+      }
+    }
+    const int rep = P.out_rep;
+    for (int dy = 0; dy < rep; dy++)
+      for (int dx = 0; dx < rep; dx++) {
+        long long opix = ((long long)n * (P.h * rep) + (y * rep + dy)) * (P.w * rep) + (x * rep + dx);
+        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(P.out_t) + opix * P.out_stride + P.out_choff + ch0);
+#pragma unroll
+        for (int i = 0; i < NCH / 8; i++) o[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tensor-core kernel
+// ---------------------------------------------------------------------------------------------
+
+struct TcSmemCtl {
+  uint64_t a_full[TC_MAX_STAGES], a_empty[TC_MAX_STAGES];
+  uint64_t w_full[TC_MAX_WBUF], w_empty[TC_MAX_WBUF];
+  uint64_t t_full[2], t_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+  float bias[64];
+};
+
+__device__ __forceinline__ void tc_fail(const ConvParams& P, int code) {
+  if (P.err_flag) atomicCAS(P.err_flag, 0, code);
+}
+
+template <bool FP16>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (ptx::smem_u32(smem) + 1023u) & ~1023u;
+  const uint32_t a_smem = smem_base;
+  const uint32_t w_smem = a_smem + P.n_stage * TC_ASTAGE;
+  const uint32_t ctl_addr = w_smem + P.n_wbuf * P.w_chunk_bytes;
+  TcSmemCtl* ctl = reinterpret_cast<TcSmemCtl*>(smem + (ctl_addr - ptx::smem_u32(smem)));
+  const int R = P.R, N = P.N;
+  const uint32_t tmem_cols = 2u * R * N <= 32 ? 32u : (2u * R * N <= 64 ? 64u : (2u * R * N <= 128 ? 128u : (2u * R * N <= 256 ? 256u : 512u)));
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&tmap);
+    for (int i = 0; i < P.n_stage; i++) {
+      ptx::mbar_init(ptx::smem_u32(&ctl->a_full[i]), 1);
+      ptx::mbar_init(ptx::smem_u32(&ctl->a_empty[i]), 1);
+    }
+    for (int i = 0; i < P.n_wbuf; i++) {
+      ptx::mbar_init(ptx::smem_u32(&ctl->w_full[i]), 1);
+      ptx::mbar_init(ptx::smem_u32(&ctl->w_empty[i]), 1);
+    }
+    for (int i = 0; i < 2; i++) {
+      ptx::mbar_init(ptx::smem_u32(&ctl->t_full[i]), 1);
+      ptx::mbar_init(ptx::smem_u32(&ctl->t_empty[i]), 4);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(ptx::smem_u32(&ctl->tmem_base), tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 128) ctl->bias[threadIdx.x - 64] = (int)(threadIdx.x - 64) < N ? P.bias[threadIdx.x - 64] : 0.0f;
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+  const int tiles_per_win = P.tiles_x * P.tiles_y;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t aphase = 0, wcount = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x, it = 0; tile < P.n_tiles && ok; tile += gridDim.x, it++) {
+        const int n = tile / tiles_per_win, tr = tile - n * tiles_per_win;
+        const int yb = tr / P.tiles_x, xr = tr - yb * P.tiles_x;
+        const int x0 = xr * TC_RUN, y0 = yb * R;
+        for (int c = 0; c < P.n_chunks && ok; c++) {
+          if (!(P.w_resident && it > 0)) {
+            const uint32_t b = wcount % P.n_wbuf, use = wcount / P.n_wbuf;
+            if (!P.w_resident) ok = ptx::mbar_wait(ptx::smem_u32(&ctl->w_empty[b]), (use & 1) ^ 1);
+            if (!ok) { tc_fail(P, 11); break; }
+            ptx::mbar_arrive_expect_tx(ptx::smem_u32(&ctl->w_full[b]), P.w_chunk_bytes);
+            ptx::bulk_load(w_smem + b * P.w_chunk_bytes, P.wpack + (size_t)c * P.w_chunk_bytes, P.w_chunk_bytes,
+                           ptx::smem_u32(&ctl->w_full[b]));
+            wcount++;
+          }
+          for (int yy = 0; yy < R + 2; yy++) {
+            ok = ptx::mbar_wait(ptx::smem_u32(&ctl->a_empty[stage]), aphase ^ 1);
+            if (!ok) { tc_fail(P, 12); break; }
+            ptx::mbar_arrive_expect_tx(ptx::smem_u32(&ctl->a_full[stage]), TC_ABYTES);
+            ptx::tma_load_4d(a_smem + stage * TC_ASTAGE, &tmap, ptx::smem_u32(&ctl->a_full[stage]), c * 64, x0 - 1,
+                             y0 - 1 + yy, n);
+            if (++stage == P.n_stage) { stage = 0; aphase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t aphase = 0, wcount = 0;
+      bool ok = true;
+      const bool stacked = P.flags & CF_STACK, baseoff = P.flags & CF_BASEOFF;
+      for (int tile = blockIdx.x, it = 0; tile < P.n_tiles && ok; tile += gridDim.x, it++) {
+        const int accbuf = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        ok = ptx::mbar_wait(ptx::smem_u32(&ctl->t_empty[accbuf]), acc_phase ^ 1);
+        if (!ok) { tc_fail(P, 21); break; }
+        ptx::tc_fence_after();
+        const uint32_t acc_base = tmem_base + accbuf * R * N;
+        for (int c = 0; c < P.n_chunks && ok; c++) {
+          int ksteps = (P.cin - c * 64) / 16;
+          if (ksteps > 4) ksteps = 4;
+          uint32_t wb;
+          if (!(P.w_resident && it > 0)) {
+            wb = wcount % P.n_wbuf;
+            ok = ptx::mbar_wait(ptx::smem_u32(&ctl->w_full[wb]), (wcount / P.n_wbuf) & 1);
+            if (!ok) { tc_fail(P, 22); break; }
+            wcount++;
+          } else {
+            wb = c;
+          }
+          ptx::tc_fence_after();
+          const uint32_t wbase = w_smem + wb * P.w_chunk_bytes;
+          for (int yy = 0; yy < R + 2; yy++) {
+            ok = ptx::mbar_wait(ptx::smem_u32(&ctl->a_full[stage]), aphase);
+            if (!ok) { tc_fail(P, 23); break; }
+            ptx::tc_fence_after();
+            const uint32_t abase = a_smem + stage * TC_ASTAGE;
+            const int jlo = yy < 2 ? 2 - yy : 0;
+            const int jhi = R + 1 - yy < 2 ? R + 1 - yy : 2;
+            for (int kx = 0; kx < 3; kx++) {
+              for (int ks = 0; ks < ksteps; ks++) {
+                const uint64_t adesc = ptx::smem_desc_sw128(abase + kx * 128 + ks * 32, 1024, baseoff ? kx : 0);
+                const uint32_t wk = wbase + kx * (3 * N * 128) + ks * 32;
+                const bool first = (c == 0 && kx == 0 && ks == 0);
+                if (stacked) {
+                  int jh = jhi;
+                  if (first && jhi == 2) {  // ky=0 block: first contribution to output row yy
+                    ptx::mma_f16_ss(acc_base + yy * N, adesc, ptx::smem_desc_sw128(wk + 2 * N * 128, 1024, 0),
+                                    P.idesc_base | ((uint32_t)(N >> 3) << 17), 0);
+                    jh = 1;
+                  }
+                  if (jlo <= jh) {
+                    const int ne = (jh - jlo + 1) * N;
+                    ptx::mma_f16_ss(acc_base + (yy - 2 + jlo) * N, adesc, ptx::smem_desc_sw128(wk + jlo * N * 128, 1024, 0),
+                                    P.idesc_base | ((uint32_t)(ne >> 3) << 17), 1);
+                  }
+                } else {
+                  for (int j = jlo; j <= jhi; j++)
+                    ptx::mma_f16_ss(acc_base + (yy - 2 + j) * N, adesc, ptx::smem_desc_sw128(wk + j * N * 128, 1024, 0),
+                                    P.idesc_base | ((uint32_t)(N >> 3) << 17), (first && j == 2) ? 0u : 1u);
+                }
+              }
+            }
+            ptx::mma_commit(ptx::smem_u32(&ctl->a_empty[stage]));
+            if (++stage == P.n_stage) { stage = 0; aphase ^= 1; }
+          }
+          if (!P.w_resident) ptx::mma_commit(ptx::smem_u32(&ctl->w_empty[wb]));
+        }
+        ptx::mma_commit(ptx::smem_u32(&ctl->t_full[accbuf]));
+      }
+    }
+  } else {
+    // ===================== epilogue warps (TMEM -> registers -> global) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    bool ok = true;
+    for (int tile = blockIdx.x, it = 0; tile < P.n_tiles && ok; tile += gridDim.x, it++) {
+      const int n = tile / tiles_per_win, tr = tile - n * tiles_per_win;
+      const int yb = tr / P.tiles_x, xr = tr - yb * P.tiles_x;
+      const int x = xr * TC_RUN + q * 32 + lane, y0 = yb * R;
+      const int accbuf = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      ok = ptx::mbar_wait(ptx::smem_u32(&ctl->t_full[accbuf]), acc_phase);
+      if (!ok) { tc_fail(P, 31); break; }
+      ptx::tc_fence_after();
+      for (int r = 0; r < R; r++) {
+        const int y = y0 + r;
+        if (y >= P.h) break;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + accbuf * R * N + r * N;
+        const bool valid = x < P.w;
+        if (N >= 32) {
+          for (int c32 = 0; c32 < N / 32; c32++) {
+            uint32_t rr[32];
+            ptx::tmem_ld32(taddr + c32 * 32, rr);
+            ptx::tmem_ld_wait();
+            if (valid) {
+              float v[32];
+#pragma unroll
+              for (int i = 0; i < 32; i++) v[i] = __uint_as_float(rr[i]);
+              epilogue_pixel<32, FP16>(P, n, y, x, c32 * 32, v, ctl->bias);
+            }
+          }
+        } else {
+          uint32_t rr[16];
+          ptx::tmem_ld16(taddr, rr);
+          ptx::tmem_ld_wait();
+          if (valid) {
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) v[i] = __uint_as_float(rr[i]);
+            epilogue_pixel<16, FP16>(P, n, y, x, 0, v, ctl->bias);
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&ctl->t_empty[accbuf]));
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// CUDA-core direct convolution with identical semantics (bring-up / cross-check)
+// ---------------------------------------------------------------------------------------------
+
+template <int N, bool FP16>
+__global__ void __launch_bounds__(128)
+conv3x3_simple_kernel(const ConvParams P) {
+  __shared__ float s_bias[64];
+  if (threadIdx.x < 64) s_bias[threadIdx.x] = (int)threadIdx.x < N ? P.bias[threadIdx.x] : 0.0f;
+  __syncthreads();
+  const long long total = (long long)P.Nw * P.h * P.w;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int x = (int)(idx % P.w);
+  const int y = (int)((idx / P.w) % P.h);
+  const int n = (int)(idx / ((long long)P.w * P.h));
+  float acc[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) acc[i] = 0.0f;
+  const uint16_t* in = reinterpret_cast<const uint16_t*>(P.in);
+  for (int ky = 0; ky < 3; ky++) {
+    const int yy = y + ky - 1;
+    if (yy < 0 || yy >= P.h) continue;
+    for (int kx = 0; kx < 3; kx++) {
+      const int xx = x + kx - 1;
+      if (xx < 0 || xx >= P.w) continue;
+      const uint16_t* ip = in + (((long long)n * P.h + yy) * P.w + xx) * P.in_stride;
+      const float* wp = P.wsimple + (long long)(ky * 3 + kx) * P.cin * N;
+      for (int ci = 0; ci < P.cin; ci++) {
+        float a;
+        if (FP16) a = __half2float(*reinterpret_cast<const __half*>(ip + ci));
+        else a = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(ip + ci));
+        const float* wr = wp + (long long)ci * N;
+#pragma unroll
+        for (int co = 0; co < N; co++) acc[co] = fmaf(a, __ldg(wr + co), acc[co]);
+      }
+    }
+  }
+  if (N >= 32) {
+#pragma unroll
+    for (int c32 = 0; c32 < N / 32; c32++) {
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; i++) v[i] = acc[c32 * 32 + i];
+      epilogue_pixel<32, FP16>(P, n, y, x, c32 * 32, v, s_bias);
+    }
+  } else {
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = acc[i];
+    epilogue_pixel<16, FP16>(P, n, y, x, 0, v, s_bias);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv_first (3 -> 64) straight from the uint8 image: x = u8/255 in fp32 (cnn_super_resolution.py:220),
+// fp32 CUDA-core convolution (K = 27 is too small for a tensor-core tile), writes the fp32 trunk
+// copies and the operand-precision copy into channels 0..63 of the dense buffer.
+// ---------------------------------------------------------------------------------------------
+
+struct FirstParams {
+  const uint8_t* img;
+  long long pitch;
+  int cin;             // 3
+  const int* win_xy;   // [Nw][2] LR origin (x0, y0) of each window in the image
+  int Nw, h, w;
+  const float* weight;  // [ky][kx][ci][64] fp32
+  const float* bias;    // [64]
+  float* f32_a;         // fp32 [pix][64] outputs (feat / trunk / rrdb_in), any may be null
+  float* f32_b;
+  float* f32_c;
+  void* out_t;
+  int out_stride;
+  float in_scale_div;   // 255 for RRDBNet
+  float sub[3];         // per-channel mean subtracted after scaling (EDSR), 0 for RRDBNet
+};
+
+template <bool FP16>
+__global__ void __launch_bounds__(128)
+conv_first_kernel(const FirstParams P) {
+  __shared__ float s_w[27 * 64];
+  __shared__ float s_b[64];
+  for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) s_w[i] = P.weight[i];
+  if (threadIdx.x < 64) s_b[threadIdx.x] = P.bias[threadIdx.x];
+  __syncthreads();
+  const long long total = (long long)P.Nw * P.h * P.w;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int qd = blockIdx.y;  // 16-channel group
+  const int x = (int)(idx % P.w);
+  const int y = (int)((idx / P.w) % P.h);
+  const int n = (int)(idx / ((long long)P.w * P.h));
+  const int wx = P.win_xy[2 * n], wy = P.win_xy[2 * n + 1];
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) acc[i] = 0.0f;
+  for (int ky = 0; ky < 3; ky++) {
+    const int yy = y + ky - 1;
+    if (yy < 0 || yy >= P.h) continue;
+    for (int kx = 0; kx < 3; kx++) {
+      const int xx = x + kx - 1;
+      if (xx < 0 || xx >= P.w) continue;
+      const uint8_t* ip = P.img + (long long)(wy + yy) * P.pitch + (long long)(wx + xx) * 3;
+#pragma unroll
+      for (int ci = 0; ci < 3; ci++) {
+        float a = __fsub_rn(__fdiv_rn((float)ip[ci], P.in_scale_div), P.sub[ci]);
+        const float* wr = s_w + ((ky * 3 + kx) * 3 + ci) * 64 + qd * 16;
+#pragma unroll
+        for (int co = 0; co < 16; co++) acc[co] = fmaf(a, wr[co], acc[co]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; i++) acc[i] += s_b[qd * 16 + i];
+  const long long pix = idx;
+  float* outs[3] = {P.f32_a, P.f32_b, P.f32_c};
+#pragma unroll
+  for (int k = 0; k < 3; k++)
+    if (outs[k]) {
+      float4* o = reinterpret_cast<float4*>(outs[k] + pix * 64 + qd * 16);
+#pragma unroll
+      for (int i = 0; i < 4; i++) o[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+    }
+  if (P.out_t) {
+    uint32_t pk[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      if (FP16) {
+        __half2 hh = __floats2half2_rn(acc[2 * i], acc[2 * i + 1]);
+        pk[i] = *reinterpret_cast<uint32_t*>(&hh);
+      } else {
+        __nv_bfloat162 bb = __floats2bfloat162_rn(acc[2 * i], acc[2 * i + 1]);
+        pk[i] = *reinterpret_cast<uint32_t*>(&bb);
+      }
+    }
+    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(P.out_t) + pix * P.out_stride + qd * 16);
+    o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  }
+}

@@ -1,0 +1,518 @@
+// WOW / farm post-process on the GPU: CLAHE (pass A histograms + LUT build) and the fused pass B
+// (LUT interpolation -> Lab->RGB -> separable fixed-point Gaussian -> unsharp -> HSV green boost).
+//
+// Replaces wow_sr._enhance_for_crops (server/app/wow_sr.py:187-209) and the farm trio
+// (server/app/farm_sr.py:61-108 as called at :170-178).  The arithmetic is OpenCV's, restated
+// exactly per SURVEY.md Appendix A: integer colour conversions, fp32 CLAHE interpolation without
+// FMA contraction, exact fixed-point blur with a single rounding, FMA in HSV->RGB.  All fp32
+// expressions that must round step by step use __fmul_rn/__fadd_rn so -fmad cannot fuse them.
+#include "common.h"
+
+namespace {
+
+struct ImgView {
+  const uint8_t* data;
+  long long pitch;
+  int W, H, y0, rows;
+};
+struct OutView {
+  uint8_t* data;
+  long long pitch;
+  int W, H, y0, rows;
+};
+
+__host__ __device__ inline int reflect101(int i, int n) {
+  if (n == 1) return 0;
+  while (i < 0 || i >= n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * n - 2 - i;
+  }
+  return i;
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// App. A.1 — only L
+__device__ __forceinline__ int rgb_to_L(int r, int g, int b, const uint16_t* gam, const uint16_t* cbrt) {
+  int R = gam[r], G = gam[g], B = gam[b];
+  int fY = cbrt[(871 * R + 2929 * G + 296 * B + 2048) >> 12];
+  return clampi((296 * fY - 1336934 + 16384) >> 15, 0, 255);
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass A: per-tile histograms of L, warp-aggregated shared-memory atomics
+// ---------------------------------------------------------------------------------------------
+
+constexpr int HIST_THREADS = 256;
+
+__global__ void __launch_bounds__(HIST_THREADS)
+clahe_hist_kernel(ImgView img, const WowsrTables* __restrict__ tabs, int grid, int tw, int th, int prow0, int prow1,
+                  int rows_per_block, int chunks_per_tile, int vec_ok, uint32_t* __restrict__ hist) {
+  __shared__ uint16_t s_gam[256];
+  __shared__ uint16_t s_cbrt[3072];
+  __shared__ uint32_t s_h[HIST_THREADS / 32][256];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tx = blockIdx.x;
+  const int ty = blockIdx.y / chunks_per_tile, chunk = blockIdx.y % chunks_per_tile;
+  int r0 = ty * th + chunk * rows_per_block;
+  int r1 = min(r0 + rows_per_block, (ty + 1) * th);
+  r0 = max(r0, prow0);
+  r1 = min(r1, prow1);
+  if (r0 >= r1) return;
+  for (int i = tid; i < 256; i += HIST_THREADS) s_gam[i] = tabs->gam[i];
+  for (int i = tid; i < 3072; i += HIST_THREADS) s_cbrt[i] = tabs->cbrt[i];
+  for (int i = tid; i < (HIST_THREADS / 32) * 256; i += HIST_THREADS) (&s_h[0][0])[i] = 0;
+  __syncthreads();
+
+  const int gpr = (tw + 3) >> 2;  // 4-pixel groups per tile row
+  const int total = (r1 - r0) * gpr;
+  const int total_up = (total + HIST_THREADS - 1) / HIST_THREADS * HIST_THREADS;
+  for (int it = tid; it < total_up; it += HIST_THREADS) {
+    uint32_t bins[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+    if (it < total) {
+      int row = r0 + it / gpr, g = it % gpr;
+      int px0 = tx * tw + g * 4;
+      int npx = min(4, tw - g * 4);
+      int sy = reflect101(row, img.H) - img.y0;
+      const uint8_t* rp = img.data + (long long)sy * img.pitch;
+      if (vec_ok && npx == 4 && px0 + 3 < img.W) {
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(rp + px0 * 3);
+        uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+        bins[0] = rgb_to_L(w0 & 255, (w0 >> 8) & 255, (w0 >> 16) & 255, s_gam, s_cbrt);
+        bins[1] = rgb_to_L(w0 >> 24, w1 & 255, (w1 >> 8) & 255, s_gam, s_cbrt);
+        bins[2] = rgb_to_L((w1 >> 16) & 255, w1 >> 24, w2 & 255, s_gam, s_cbrt);
+        bins[3] = rgb_to_L((w2 >> 8) & 255, (w2 >> 16) & 255, w2 >> 24, s_gam, s_cbrt);
+      } else {
+        for (int k = 0; k < npx; k++) {
+          int sx = reflect101(px0 + k, img.W);
+          const uint8_t* p = rp + sx * 3;
+          bins[k] = rgb_to_L(__ldg(p), __ldg(p + 1), __ldg(p + 2), s_gam, s_cbrt);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      uint32_t bin = bins[k];
+      unsigned m = __match_any_sync(0xFFFFFFFFu, bin);
+      if (bin != 0xFFFFFFFFu && lane == __ffs(m) - 1) atomicAdd(&s_h[warp][bin], (uint32_t)__popc(m));
+    }
+  }
+  __syncthreads();
+  for (int b = tid; b < 256; b += HIST_THREADS) {
+    uint32_t s = 0;
+#pragma unroll
+    for (int w = 0; w < HIST_THREADS / 32; w++) s += s_h[w][b];
+    if (s) atomicAdd(&hist[(ty * grid + tx) * 256 + b], s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LUT build: clip, redistribute, cumulative sum, scale (App. A.2)
+// ---------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256)
+clahe_lut_kernel(const uint32_t* __restrict__ hist, int clip_limit, float lut_scale, uint8_t* __restrict__ luts) {
+  __shared__ uint32_t s_red[8];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  uint32_t h = hist[blockIdx.x * 256 + t];
+  uint32_t excess = h > (uint32_t)clip_limit ? h - clip_limit : 0;
+  if (h > (uint32_t)clip_limit) h = clip_limit;
+  uint32_t e = excess;
+  for (int o = 16; o; o >>= 1) e += __shfl_xor_sync(0xFFFFFFFFu, e, o);
+  if (lane == 0) s_red[warp] = e;
+  __syncthreads();
+  uint32_t clipped = 0;
+  for (int w = 0; w < 8; w++) clipped += s_red[w];
+  uint32_t batch = clipped >> 8;
+  uint32_t resid = clipped - (batch << 8);
+  h += batch;
+  if (resid) {
+    uint32_t step = 256 / resid;
+    if (step < 1) step = 1;
+    if (t % step == 0 && t / step < resid) h++;
+  }
+  // inclusive scan over 256 bins
+  uint32_t v = h;
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t n = __shfl_up_sync(0xFFFFFFFFu, v, o);
+    if (lane >= o) v += n;
+  }
+  __syncthreads();
+  if (lane == 31) s_red[warp] = v;
+  __syncthreads();
+  uint32_t base = 0;
+  for (int w = 0; w < warp; w++) base += s_red[w];
+  v += base;
+  int q = __float2int_rn(__fmul_rn(__uint2float_rn(v), lut_scale));
+  luts[blockIdx.x * 256 + t] = (uint8_t)clampi(q, 0, 255);
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass B
+// ---------------------------------------------------------------------------------------------
+
+constexpr int PB_TX = 64, PB_TY = 64, PB_THREADS = 256, PB_MAXR = 8;
+
+struct PostK {
+  int stages;
+  int grid, tw, th;
+  float inv_tw, inv_th;
+  int r;                 // effective blur radius (outermost non-zero tap)
+  int taps[2 * PB_MAXR + 1];
+  float alpha, beta;
+  int hue_lo, hue_hi;
+  float sat;
+  float inv255, hscale;
+  int tail_x;            // first column handled by cv2's scalar HSV->RGB tail (W - W%32)
+};
+
+struct SmemTabs {
+  uint16_t gam[256];
+  uint16_t cbrt[3072];
+  uint16_t lab_y[256];
+  uint16_t lab_ify[256];
+  uint8_t invgam[4096];
+  uint32_t sdiv[256];
+  uint32_t hdiv[256];
+};
+
+__device__ __forceinline__ int ab2xz(int i) {
+  // App. A.3: C integer division truncates toward zero
+  if (i <= 3390) return (i * 108) / 841 - 290;
+  return ((i * i) / 16384 * i) / 16384;
+}
+
+__device__ __forceinline__ int ds(int x, int n) { return (x + (1 << (n - 1))) >> n; }
+
+// CLAHE + Lab round trip for one pixel at image position (x, y): returns packed r | g<<8 | b<<16
+__device__ __forceinline__ uint32_t enhance_pixel(int r, int g, int b, int x, int y, const PostK& k,
+                                                  const SmemTabs& T, const uint8_t* __restrict__ luts) {
+  // RGB -> Lab (A.1)
+  int R = T.gam[r], G = T.gam[g], B = T.gam[b];
+  int fX = T.cbrt[ds(1777 * R + 1541 * G + 778 * B, 12)];
+  int fY = T.cbrt[ds(871 * R + 2929 * G + 296 * B, 12)];
+  int fZ = T.cbrt[ds(73 * R + 448 * G + 3575 * B, 12)];
+  int L = clampi(ds(296 * fY - 1336934, 15), 0, 255);
+  int a = clampi(ds(500 * (fX - fY) + 128 * 32768, 15), 0, 255);
+  int bb = clampi(ds(200 * (fY - fZ) + 128 * 32768, 15), 0, 255);
+  // CLAHE bilinear LUT interpolation (A.2), fp32 with separately rounded operations
+  float txf = __fsub_rn(__fmul_rn((float)x, k.inv_tw), 0.5f);
+  float tyf = __fsub_rn(__fmul_rn((float)y, k.inv_th), 0.5f);
+  int tx1 = (int)floorf(txf), ty1 = (int)floorf(tyf);
+  float xa = __fsub_rn(txf, (float)tx1), ya = __fsub_rn(tyf, (float)ty1);
+  float xa1 = __fsub_rn(1.0f, xa), ya1 = __fsub_rn(1.0f, ya);
+  int tx2 = min(tx1 + 1, k.grid - 1), ty2 = min(ty1 + 1, k.grid - 1);
+  tx1 = max(tx1, 0);
+  ty1 = max(ty1, 0);
+  float p00 = (float)__ldg(luts + ((ty1 * k.grid + tx1) << 8) + L);
+  float p01 = (float)__ldg(luts + ((ty1 * k.grid + tx2) << 8) + L);
+  float p10 = (float)__ldg(luts + ((ty2 * k.grid + tx1) << 8) + L);
+  float p11 = (float)__ldg(luts + ((ty2 * k.grid + tx2) << 8) + L);
+  float top = __fadd_rn(__fmul_rn(p00, xa1), __fmul_rn(p01, xa));
+  float bot = __fadd_rn(__fmul_rn(p10, xa1), __fmul_rn(p11, xa));
+  float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
+  L = clampi(__float2int_rn(res), 0, 255);
+  // Lab -> RGB (A.3)
+  int yy = T.lab_y[L], ify = T.lab_ify[L];
+  int adiv = ((5 * a * 53687 + 128) >> 13) - 4194;
+  int bdiv = ((bb * 41943 + 16) >> 9) - 10485 + 1;
+  int X = ab2xz(ify + adiv), Z = ab2xz(ify - bdiv);
+  int ro = clampi(ds(12615 * X - 6296 * yy - 2223 * Z, 14), 0, 4095);
+  int go = clampi(ds(-3773 * X + 7684 * yy + 185 * Z, 14), 0, 4095);
+  int bo = clampi(ds(217 * X - 836 * yy + 4715 * Z, 14), 0, 4095);
+  return (uint32_t)T.invgam[ro] | ((uint32_t)T.invgam[go] << 8) | ((uint32_t)T.invgam[bo] << 16);
+}
+
+// RGB -> HSV -> green boost -> HSV -> RGB (A.6 + glue wow_sr.py:200-207)
+__device__ __forceinline__ uint32_t vegetation_pixel(int r, int g, int b, bool tail, const PostK& k, const SmemTabs& T) {
+  int v = max(max(r, g), b), mn = min(min(r, g), b);
+  int diff = v - mn;
+  int s = (int)((diff * T.sdiv[v] + 2048u) >> 12);
+  int h;
+  if (v == r) h = g - b;
+  else if (v == g) h = b - r + 2 * diff;
+  else h = r - g + 4 * diff;
+  h = (h * (int)T.hdiv[diff] + 2048) >> 12;
+  if (h < 0) h += 180;
+  if (h > k.hue_lo && h < k.hue_hi) s = (int)fminf(__fmul_rn((float)s, k.sat), 255.0f);
+  // HSV -> RGB: FMA inside 1 - s*f, plain multiplies outside
+  float sf = __fmul_rn((float)s, k.inv255), vf = __fmul_rn((float)v, k.inv255);
+  float h6 = __fmul_rn((float)h, k.hscale);
+  float secf = floorf(h6);
+  float f = __fsub_rn(h6, secf);
+  int sec = (int)secf;
+  if (sec >= 6) sec -= 6;
+  float t0 = vf;
+  float t1 = __fmul_rn(vf, __fsub_rn(1.0f, sf));
+  float t2 = __fmul_rn(vf, __fmaf_rn(-sf, f, 1.0f));
+  float t3 = __fmul_rn(vf, __fmaf_rn(-sf, __fsub_rn(1.0f, f), 1.0f));
+  float bq, gq, rq;
+  switch (sec) {
+    case 0: bq = t1; gq = t3; rq = t0; break;
+    case 1: bq = t1; gq = t0; rq = t2; break;
+    case 2: bq = t3; gq = t0; rq = t1; break;
+    case 3: bq = t0; gq = t2; rq = t1; break;
+    case 4: bq = t0; gq = t1; rq = t3; break;
+    default: bq = t2; gq = t1; rq = t0; break;
+  }
+  rq = __fmul_rn(rq, 255.0f);
+  gq = __fmul_rn(gq, 255.0f);
+  bq = __fmul_rn(bq, 255.0f);
+  int ri, gi, bi;
+  if (tail) {  // cv2's scalar row tail rounds (saturate_cast) where its SIMD body truncates
+    ri = __float2int_rn(rq); gi = __float2int_rn(gq); bi = __float2int_rn(bq);
+  } else {
+    ri = (int)rq; gi = (int)gq; bi = (int)bq;
+  }
+  return (uint32_t)clampi(ri, 0, 255) | ((uint32_t)clampi(gi, 0, 255) << 8) | ((uint32_t)clampi(bi, 0, 255) << 16);
+}
+
+__global__ void __launch_bounds__(PB_THREADS)
+post_apply_kernel(ImgView img, OutView out, const WowsrTables* __restrict__ tabs, const uint8_t* __restrict__ luts,
+                  PostK k, int row0, int row1, int tiles_x, int n_tiles) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  SmemTabs& T = *reinterpret_cast<SmemTabs*>(smem_raw);
+  const int r = k.r;
+  const int EW = PB_TX + 2 * r, EH = PB_TY + 2 * r;
+  uint32_t* E = reinterpret_cast<uint32_t*>(smem_raw + ((sizeof(SmemTabs) + 15) & ~15));  // [EH][EW] packed rgb
+  uint2* Hs = reinterpret_cast<uint2*>(E + EH * EW + ((EH * EW) & 1));                    // [EH][PB_TX] 3 x u16 (+pad)
+  const int tid = threadIdx.x;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(tabs);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&T);
+    for (int i = tid; i < (int)(sizeof(SmemTabs) / 4); i += PB_THREADS) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int bx = (tile % tiles_x) * PB_TX;
+    const int by = row0 + (tile / tiles_x) * PB_TY;
+    // stage 1: enhanced RGB for the halo tile (reflect-101 at the image borders)
+    for (int i = tid; i < EH * EW; i += PB_THREADS) {
+      int ey = i / EW, ex = i - ey * EW;
+      int gx = reflect101(bx - r + ex, img.W), gy = reflect101(by - r + ey, img.H);
+      int gyb = gy - img.y0;
+      if (gyb < 0 || gyb >= img.rows) {  // tile overhang beyond the band: never consumed
+        E[i] = 0;
+        continue;
+      }
+      const uint8_t* p = img.data + (long long)gyb * img.pitch + gx * 3;
+      int cr = __ldg(p), cg = __ldg(p + 1), cb = __ldg(p + 2);
+      uint32_t e = (k.stages & WOWSR_STAGE_CLAHE) ? enhance_pixel(cr, cg, cb, gx, gy, k, T, luts)
+                                                  : ((uint32_t)cr | ((uint32_t)cg << 8) | ((uint32_t)cb << 16));
+      E[i] = e;
+    }
+    __syncthreads();
+    if (k.stages & WOWSR_STAGE_UNSHARP) {
+      // stage 2: horizontal pass, exact in u16
+      for (int i = tid; i < EH * PB_TX; i += PB_THREADS) {
+        int ey = i / PB_TX, x = i - ey * PB_TX;
+        const uint32_t* e = E + ey * EW + x;
+        uint32_t ar = 0, ag = 0, ab = 0;
+        for (int t = 0; t <= 2 * r; t++) {
+          uint32_t px = e[t];
+          uint32_t w = k.taps[t];
+          ar += w * (px & 255);
+          ag += w * ((px >> 8) & 255);
+          ab += w * ((px >> 16) & 255);
+        }
+        Hs[i] = make_uint2(ar | (ag << 16), ab);
+      }
+      __syncthreads();
+    }
+    // stage 3: vertical pass + unsharp + vegetation, one pixel per thread iteration
+    for (int i = tid; i < PB_TX * PB_TY; i += PB_THREADS) {
+      int y = i / PB_TX, x = i - y * PB_TX;
+      int gx = bx + x, gy = by + y;
+      if (gx >= img.W || gy >= row1) continue;
+      uint32_t e = E[(y + r) * EW + x + r];
+      int cr = e & 255, cg = (e >> 8) & 255, cb = (e >> 16) & 255;
+      if (k.stages & WOWSR_STAGE_UNSHARP) {
+        uint32_t ar = 0, ag = 0, ab = 0;
+        for (int t = 0; t <= 2 * r; t++) {
+          uint2 hv = Hs[(y + t) * PB_TX + x];
+          uint32_t w = k.taps[t];
+          ar += w * (hv.x & 0xFFFF);
+          ag += w * (hv.x >> 16);
+          ab += w * (hv.y & 0xFFFF);
+        }
+        int br = (ar + 32768) >> 16, bg = (ag + 32768) >> 16, bb = (ab + 32768) >> 16;
+        cr = clampi(__float2int_rn(__fadd_rn(__fmul_rn((float)cr, k.alpha), __fmul_rn((float)br, k.beta))), 0, 255);
+        cg = clampi(__float2int_rn(__fadd_rn(__fmul_rn((float)cg, k.alpha), __fmul_rn((float)bg, k.beta))), 0, 255);
+        cb = clampi(__float2int_rn(__fadd_rn(__fmul_rn((float)cb, k.alpha), __fmul_rn((float)bb, k.beta))), 0, 255);
+      }
+      uint32_t o = (uint32_t)cr | ((uint32_t)cg << 8) | ((uint32_t)cb << 16);
+      if (k.stages & WOWSR_STAGE_VEG) o = vegetation_pixel(cr, cg, cb, gx >= k.tail_x, k, T);
+      uint8_t* q = out.data + (long long)(gy - out.y0) * out.pitch + gx * 3;
+      q[0] = (uint8_t)(o & 255);
+      q[1] = (uint8_t)((o >> 8) & 255);
+      q[2] = (uint8_t)(o >> 16);
+    }
+    __syncthreads();
+  }
+}
+
+size_t post_smem_bytes(int r) {
+  int EW = PB_TX + 2 * r, EH = PB_TY + 2 * r;
+  size_t s = (sizeof(SmemTabs) + 15) & ~(size_t)15;
+  s += (size_t)(EH * EW + ((EH * EW) & 1)) * 4;
+  s += (size_t)EH * PB_TX * 8;
+  return s;
+}
+
+int check_image(wowsr_ctx* ctx, const wowsr_image* im, const char* what) {
+  if (!im || !im->data || im->W <= 0 || im->H <= 0 || im->rows <= 0 || im->y0 < 0 || im->y0 + im->rows > im->H ||
+      im->pitch < (int64_t)im->W * 3)
+    return wowsr_fail(ctx, WOWSR_ERR_ARG, "bad %s image descriptor", what);
+  return 0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+
+extern "C" int wowsr_clahe_hist(wowsr_ctx* ctx, const wowsr_image* rgb, int32_t grid, int32_t prow0, int32_t prow1,
+                                uint32_t* hist_dev, void* stream) {
+  if (!ctx) return WOWSR_ERR_ARG;
+  if (int e = check_image(ctx, rgb, "input")) return e;
+  if (grid < 1 || grid > 64 || !hist_dev) return wowsr_fail(ctx, WOWSR_ERR_ARG, "bad grid/hist");
+  DeviceGuard g(ctx->device);
+  int tw, th, pw, ph;
+  wowsr_clahe_geometry(rgb->H, rgb->W, grid, &tw, &th, &pw, &ph);
+  if (prow0 < 0) prow0 = 0;
+  if (prow1 > ph) prow1 = ph;
+  if (prow0 >= prow1) return WOWSR_OK;
+  // the band must hold every source row the padded range maps to
+  for (int pr : {prow0, prow1 - 1}) {
+    int sy = reflect101(pr, rgb->H);
+    if (sy < rgb->y0 || sy >= rgb->y0 + rgb->rows)
+      return wowsr_fail(ctx, WOWSR_ERR_ARG, "band [%d,%d) does not hold source row %d", rgb->y0, rgb->y0 + rgb->rows, sy);
+  }
+  int target_chunks = (4 * ctx->sm_count + grid * grid - 1) / (grid * grid);
+  int rows_per_block = (th + target_chunks - 1) / target_chunks;
+  if (rows_per_block < 1) rows_per_block = 1;
+  int chunks = (th + rows_per_block - 1) / rows_per_block;
+  ImgView v{(const uint8_t*)rgb->data, rgb->pitch, rgb->W, rgb->H, rgb->y0, rgb->rows};
+  int vec_ok = (rgb->pitch % 4 == 0) && (((uintptr_t)rgb->data) % 4 == 0) && (tw % 4 == 0);
+  dim3 gr(grid, grid * chunks);
+  clahe_hist_kernel<<<gr, HIST_THREADS, 0, (cudaStream_t)stream>>>(v, ctx->d_tables, grid, tw, th, prow0, prow1,
+                                                                    rows_per_block, chunks, vec_ok, hist_dev);
+  WLAUNCH_CHECK(ctx);
+  return WOWSR_OK;
+}
+
+extern "C" int wowsr_clahe_luts(wowsr_ctx* ctx, const uint32_t* hist_dev, int32_t grid, int32_t tile_w, int32_t tile_h,
+                                double clip_limit, uint8_t* luts_dev, void* stream) {
+  if (!ctx || !hist_dev || !luts_dev || grid < 1 || tile_w < 1 || tile_h < 1) return WOWSR_ERR_ARG;
+  DeviceGuard g(ctx->device);
+  int area = tile_w * tile_h;
+  // cv2: clipLimit = max(int(clip * tileSizeTotal / histSize), 1), evaluated in double
+  int clip = 0x7FFFFFFF;
+  if (clip_limit > 0.0) {
+    clip = (int)(clip_limit * area / 256.0);
+    if (clip < 1) clip = 1;
+  }
+  float lut_scale = 255.0f / (float)area;
+  clahe_lut_kernel<<<grid * grid, 256, 0, (cudaStream_t)stream>>>(hist_dev, clip, lut_scale, luts_dev);
+  WLAUNCH_CHECK(ctx);
+  return WOWSR_OK;
+}
+
+extern "C" int wowsr_post_apply(wowsr_ctx* ctx, const wowsr_image* rgb, const uint8_t* luts_dev,
+                                const wowsr_post_params* p, int32_t row0, int32_t row1, const wowsr_image* out,
+                                void* stream) {
+  if (!ctx || !p) return WOWSR_ERR_ARG;
+  if (int e = check_image(ctx, rgb, "input")) return e;
+  if (int e = check_image(ctx, out, "output")) return e;
+  if (out->W != rgb->W || out->H != rgb->H) return wowsr_fail(ctx, WOWSR_ERR_ARG, "input/output size mismatch");
+  if ((p->stages & WOWSR_STAGE_CLAHE) && !luts_dev) return wowsr_fail(ctx, WOWSR_ERR_ARG, "CLAHE stage needs luts");
+  DeviceGuard g(ctx->device);
+  PostK k;
+  memset(&k, 0, sizeof k);
+  k.stages = p->stages;
+  k.grid = p->grid;
+  int pw, ph;
+  wowsr_clahe_geometry(rgb->H, rgb->W, p->grid, &k.tw, &k.th, &pw, &ph);
+  k.inv_tw = 1.0f / (float)k.tw;
+  k.inv_th = 1.0f / (float)k.th;
+  k.r = 0;
+  if (p->stages & WOWSR_STAGE_UNSHARP) {
+    int taps[32];
+    int ks = wowsr_gaussian_taps(p->sigma, taps, 32);
+    if (ks < 0) return wowsr_fail(ctx, WOWSR_ERR_UNSUPPORTED, "sigma %f gives a kernel wider than 31", p->sigma);
+    int half = ks / 2, r = half;
+    while (r > 0 && taps[half - r] == 0) r--;
+    if (r > PB_MAXR) return wowsr_fail(ctx, WOWSR_ERR_UNSUPPORTED, "blur radius %d > %d", r, PB_MAXR);
+    k.r = r;
+    for (int t = 0; t <= 2 * r; t++) k.taps[t] = taps[half - r + t];
+  }
+  k.alpha = p->alpha;
+  k.beta = p->beta;
+  k.hue_lo = p->hue_lo;
+  k.hue_hi = p->hue_hi;
+  k.sat = p->sat_boost;
+  k.inv255 = (float)(1.0 / 255.0);
+  k.hscale = (float)(6.0 / 180.0);
+  k.tail_x = rgb->W - rgb->W % 32;
+  if (row0 < 0) row0 = 0;
+  if (row1 > rgb->H) row1 = rgb->H;
+  if (row0 >= row1) return WOWSR_OK;
+  int need0 = row0 - k.r < 0 ? 0 : row0 - k.r, need1 = row1 + k.r > rgb->H ? rgb->H : row1 + k.r;
+  if (need0 < rgb->y0 || need1 > rgb->y0 + rgb->rows)
+    return wowsr_fail(ctx, WOWSR_ERR_ARG, "input band [%d,%d) lacks halo rows [%d,%d)", rgb->y0, rgb->y0 + rgb->rows, need0, need1);
+  if (row0 < out->y0 || row1 > out->y0 + out->rows) return wowsr_fail(ctx, WOWSR_ERR_ARG, "output band too small");
+  ImgView iv{(const uint8_t*)rgb->data, rgb->pitch, rgb->W, rgb->H, rgb->y0, rgb->rows};
+  OutView ov{(uint8_t*)out->data, out->pitch, out->W, out->H, out->y0, out->rows};
+  int tiles_x = (rgb->W + PB_TX - 1) / PB_TX, tiles_y = (row1 - row0 + PB_TY - 1) / PB_TY;
+  int n_tiles = tiles_x * tiles_y;
+  size_t smem = post_smem_bytes(k.r);
+  static_assert(sizeof(SmemTabs) == sizeof(WowsrTables), "table layouts must match");
+  WCUDA(ctx, cudaFuncSetAttribute(post_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = (int)(200 * 1024 / smem);
+  if (per_sm < 1) per_sm = 1;
+  int blocks = ctx->sm_count * per_sm;
+  if (blocks > n_tiles) blocks = n_tiles;
+  post_apply_kernel<<<blocks, PB_THREADS, smem, (cudaStream_t)stream>>>(iv, ov, ctx->d_tables, luts_dev, k, row0, row1,
+                                                                        tiles_x, n_tiles);
+  WLAUNCH_CHECK(ctx);
+  return WOWSR_OK;
+}
+
+extern "C" int wowsr_post_process_dev(wowsr_ctx* ctx, const wowsr_image* rgb, const wowsr_post_params* p,
+                                      const wowsr_image* out, void* stream) {
+  if (!ctx || !p) return WOWSR_ERR_ARG;
+  if (int e = check_image(ctx, rgb, "input")) return e;
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint8_t* luts = nullptr;
+  if (p->stages & WOWSR_STAGE_CLAHE) {
+    int n = p->grid * p->grid * 256;
+    if (int e = wowsr_ensure(ctx, ctx->hist, (size_t)n * 4)) return e;
+    if (int e = wowsr_ensure(ctx, ctx->luts, (size_t)n)) return e;
+    WCUDA(ctx, cudaMemsetAsync(ctx->hist.p, 0, (size_t)n * 4, st));
+    int tw, th, pw, ph;
+    wowsr_clahe_geometry(rgb->H, rgb->W, p->grid, &tw, &th, &pw, &ph);
+    if (int e = wowsr_clahe_hist(ctx, rgb, p->grid, 0, ph, (uint32_t*)ctx->hist.p, stream)) return e;
+    if (int e = wowsr_clahe_luts(ctx, (const uint32_t*)ctx->hist.p, p->grid, tw, th, p->clip_limit, (uint8_t*)ctx->luts.p, stream))
+      return e;
+    luts = (const uint8_t*)ctx->luts.p;
+  }
+  return wowsr_post_apply(ctx, rgb, luts, p, 0, rgb->H, out, stream);
+}
+
+extern "C" int wowsr_post_process_host(wowsr_ctx* ctx, const uint8_t* rgb_host, int32_t H, int32_t W,
+                                       const wowsr_post_params* p, uint8_t* out_host) {
+  if (!ctx || !rgb_host || !out_host || !p || H <= 0 || W <= 0) return WOWSR_ERR_ARG;
+  DeviceGuard g(ctx->device);
+  size_t pitch = ((size_t)W * 3 + 15) & ~(size_t)15;
+  if (int e = wowsr_ensure(ctx, ctx->post_in, pitch * H)) return e;
+  if (int e = wowsr_ensure(ctx, ctx->post_out, pitch * H)) return e;
+  WCUDA(ctx, cudaMemcpy2DAsync(ctx->post_in.p, pitch, rgb_host, (size_t)W * 3, (size_t)W * 3, H, cudaMemcpyHostToDevice, 0));
+  wowsr_image in{ctx->post_in.p, (int64_t)pitch, W, H, 0, H};
+  wowsr_image out{ctx->post_out.p, (int64_t)pitch, W, H, 0, H};
+  if (int e = wowsr_post_process_dev(ctx, &in, p, &out, nullptr)) return e;
+  WCUDA(ctx, cudaMemcpy2DAsync(out_host, (size_t)W * 3, ctx->post_out.p, pitch, (size_t)W * 3, H, cudaMemcpyDeviceToHost, 0));
+  WCUDA(ctx, cudaStreamSynchronize(0));
+  return WOWSR_OK;
+}
