@@ -1,0 +1,99 @@
+"""GPU: post-process kernels through the C ABI vs the oracle (bit-exact bar)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import postproc_np as P
+from oracle import wow_cv2
+from tests.conftest import image_like
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_goldens_from_reference(ws, handle):
+    g = np.load(os.path.join(GOLD, "post_wow_96x128.npz"))
+    assert np.array_equal(ws.app.wow_sr._enhance_for_crops(g["img"]), g["out"])
+    g = np.load(os.path.join(GOLD, "post_farm_101x77.npz"))
+    assert np.array_equal(ws.app.farm_sr.farm_post(g["img"]), g["out"])
+    img = g["img"]
+    f = ws.app.farm_sr
+    step = f.enhance_vegetation(f.apply_unsharp_mask(f.enhance_local_contrast(img, clip_limit=2.5, grid_size=8), strength=1.2, radius=1.5))
+    assert np.array_equal(step, g["out"])          # the trio called one by one == fused pass == reference
+
+
+@pytest.mark.parametrize("shape", [(64, 64), (512, 512), (517, 1003), (300, 200), (1104, 1104), (9, 40), (2304, 1728)])
+def test_full_chain_bit_exact(ws, handle, shape):
+    img = image_like(*shape, seed=shape[0])
+    assert np.array_equal(handle.post_process_host(img, ws._lib.post_params("wow")), wow_cv2.enhance_for_crops(img))
+    assert np.array_equal(handle.post_process_host(img, ws._lib.post_params("farm")), wow_cv2.farm_post(img))
+
+
+def test_farm_trio_defaults(ws, handle):
+    img = image_like(203, 310, seed=9)
+    f = ws.app.farm_sr
+    assert np.array_equal(f.enhance_local_contrast(img), P.enhance_local_contrast(img, 3.0, 8))
+    assert np.array_equal(f.apply_unsharp_mask(img), P.apply_unsharp_mask(img, 1.5, 1.0))
+    assert np.array_equal(f.enhance_vegetation(img), P.enhance_vegetation(img))
+
+
+@pytest.mark.parametrize("shape", [(512, 512), (517, 1003), (4096, 4096)])
+def test_clahe_hist_and_luts_bit_exact(ws, handle, shape):
+    import torch
+    img = image_like(*shape, seed=7)
+    H, W = shape
+    d = torch.from_numpy(img).cuda()
+    tw, th, pw, ph = ws._lib.clahe_geometry(H, W, 8)
+    hist = torch.zeros(64 * 256, dtype=torch.int32, device="cuda")
+    luts = torch.zeros(64 * 256, dtype=torch.uint8, device="cuda")
+    im = ws._lib.Image(d.data_ptr(), W * 3, W, H, 0, H)
+    handle.clahe_hist(im, 8, 0, ph, hist.data_ptr())
+    handle.clahe_luts(hist.data_ptr(), 8, tw, th, 2.5, luts.data_ptr())
+    torch.cuda.synchronize()
+    L = P.rgb2l_u8(img)
+    ref_hist = P.clahe_hist(L, 8)
+    assert np.array_equal(hist.cpu().numpy().astype(np.uint32).reshape(8, 8, 256), ref_hist)
+    assert np.array_equal(luts.cpu().numpy().reshape(8, 8, 256), P.clahe_luts(ref_hist, tw * th, 2.5))
+    assert int(hist.sum()) == pw * ph
+
+
+def test_band_split_equals_whole(ws, handle):
+    """Multi-GPU decomposition on one GPU: two bands (+halo) with summed histograms == whole image."""
+    import torch
+    H, W = 1100, 900
+    img = image_like(H, W, seed=21)
+    p = ws._lib.post_params("farm")
+    want = wow_cv2.farm_post(img)
+    tw, th, pw, ph = ws._lib.clahe_geometry(H, W, 8)
+    d = torch.from_numpy(img).cuda()
+    hist = torch.zeros(64 * 256, dtype=torch.int32, device="cuda")
+    luts = torch.zeros(64 * 256, dtype=torch.uint8, device="cuda")
+    split, r = 537, 4
+    bands = [(0, split), (split, H)]
+    for (a, b) in bands:                                   # each "rank" sees only its own rows
+        sub = d[a:b].contiguous()
+        im = ws._lib.Image(sub.data_ptr(), W * 3, W, H, a, b - a)
+        handle.clahe_hist(im, 8, a, b if b < H else ph, hist.data_ptr())
+    handle.clahe_luts(hist.data_ptr(), 8, tw, th, 2.5, luts.data_ptr())
+    out = torch.zeros_like(d)
+    for (a, b) in bands:
+        lo, hi = max(a - r, 0), min(b + r, H)               # halo rows from the neighbour
+        sub = d[lo:hi].contiguous()
+        src = ws._lib.Image(sub.data_ptr(), W * 3, W, H, lo, hi - lo)
+        dst_t = out[a:b]
+        dst = ws._lib.Image(dst_t.data_ptr(), W * 3, W, H, a, b - a)
+        handle.post_apply(src, luts.data_ptr(), p, a, b, dst)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), want)
+
+
+def test_idempotent_launch_and_error_paths(ws, handle):
+    img = image_like(64, 64)
+    a = handle.post_process_host(img, ws._lib.post_params("wow"))
+    b = handle.post_process_host(img, ws._lib.post_params("wow"))
+    assert np.array_equal(a, b)
+    with pytest.raises(ValueError):
+        handle.post_process_host(img[..., 0], ws._lib.post_params("wow"))
+    with pytest.raises(ws.WowsrError):
+        handle.post_process_host(img, ws._lib.post_params("wow", sigma=9.0))
