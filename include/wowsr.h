@@ -146,6 +146,7 @@ int32_t wowsr_plan_windows(int32_t H, int32_t W, int32_t tile, int32_t pad, wows
 
 #define WOWSR_PREC_BF16 0      /* bf16 operands, fp32 accumulate, fp32 residual trunk */
 #define WOWSR_PREC_FP16 1      /* fp16 operands, fp32 accumulate, fp32 residual trunk */
+#define WOWSR_PREC_MIXED 2     /* bf16 RRDB trunk (92 % of the FLOPs) + fp16 for the 5 tail convs; default */
 
 /* Loads weights.  `tensors` are host fp32 pointers in the order of the reference state_dict
  * (conv_first.weight, conv_first.bias, body.0.rdb1.conv1.weight, ... conv_last.bias; weights

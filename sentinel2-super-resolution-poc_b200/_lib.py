@@ -11,7 +11,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwowsr.so")
 
-PREC = {"bf16": 0, "fp16": 1}
+PREC = {"bf16_pure": 0, "fp16": 1, "bf16": 2, "mixed": 2}
 
 
 class PostParams(C.Structure):

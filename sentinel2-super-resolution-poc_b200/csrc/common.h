@@ -37,6 +37,7 @@ struct wowsr_ctx {
   int sm_count = 148;
   std::string err;
   uint64_t launches = 0;
+  bool tc_attr_set = false;
   WowsrTables* d_tables = nullptr;
   std::map<std::string, int64_t> opts;
   // post-process scratch

@@ -18,6 +18,7 @@ constexpr size_t SMEM_SLACK = 1024 + 1024;  // alignment slack + control block
 struct LayerW {
   int cin = 0, cout = 0, N = 0, n_chunks = 0;
   size_t chunk_bytes = 0;
+  bool fp16 = false;  // operand type of this layer (input activations and weights)
   uint8_t* wpack = nullptr;
   float* wsimple = nullptr;
   float* bias = nullptr;
@@ -28,7 +29,7 @@ struct LayerW {
 struct ConvNet {
   int kind = 0;  // 0 RRDBNet, 1 EDSR
   int num_block = 0, nf = 64, gc = 32;
-  bool fp16 = false;
+  bool body_fp16 = false, tail_fp16 = false;  // operand types: RRDB trunk / the 5 tail convs
   float res_scale = 1.0f;
   float* first_w = nullptr;  // [ky][kx][ci][64] fp32
   float* first_b = nullptr;
@@ -72,6 +73,7 @@ int pad_n(int cout) { return cout <= 16 ? 16 : (cout <= 32 ? 32 : 64); }
 int upload_layer(wowsr_ctx* ctx, LayerW& L, const float* w, const float* b, int cin, int cout, bool fp16) {
   if (cin % 16 != 0 || cout > 64 || cout < 1) return wowsr_fail(ctx, WOWSR_ERR_UNSUPPORTED, "conv %d->%d unsupported", cin, cout);
   L.cin = cin;
+  L.fp16 = fp16;
   L.cout = cout;
   L.N = pad_n(cout);
   L.n_chunks = (cin + 63) / 64;
@@ -167,6 +169,7 @@ struct LayerIO {
   float* out_f32_b = nullptr;
   void* out_t = nullptr;
   int out_stride = 0, out_choff = 0, out_rep = 1;
+  int out_fp16 = 0;
   int final = 0;
   uint8_t* out_u8 = nullptr;
   long long out_u8_pitch = 0;
@@ -189,8 +192,8 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
   P.tiles_x = (io.w + TC_RUN - 1) / TC_RUN;
   P.tiles_y = (io.h + R - 1) / R;
   P.n_tiles = P.tiles_x * P.tiles_y * io.Nw;
-  P.flags = (int)wowsr_opt(ctx, "tc_flags", CF_STACK) | (net->fp16 ? CF_FP16 : 0);
-  P.idesc_base = make_idesc_f16(128, 0, net->fp16);
+  P.flags = (int)wowsr_opt(ctx, "tc_flags", CF_STACK) | (L.fp16 ? CF_FP16 : 0) | (io.out_fp16 ? CF_OUT_FP16 : 0);
+  P.idesc_base = make_idesc_f16(128, 0, L.fp16);
   P.w_chunk_bytes = (uint32_t)L.chunk_bytes;
   size_t wtotal = L.chunk_bytes * L.n_chunks;
   if (wtotal + 4 * (size_t)TC_ASTAGE + SMEM_SLACK <= SMEM_LIMIT && L.n_chunks <= TC_MAX_WBUF &&
@@ -221,26 +224,23 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
     long long total = (long long)io.Nw * io.h * io.w;
     unsigned blocks = (unsigned)((total + 127) / 128);
 #define SIMPLE(NN)                                                                              \
-  if (net->fp16) conv3x3_simple_kernel<NN, true><<<blocks, 128, 0, st>>>(P);                    \
-  else conv3x3_simple_kernel<NN, false><<<blocks, 128, 0, st>>>(P);
+  conv3x3_simple_kernel<NN><<<blocks, 128, 0, st>>>(P);
     if (N == 16) { SIMPLE(16) } else if (N == 32) { SIMPLE(32) } else { SIMPLE(64) }
 #undef SIMPLE
     WLAUNCH_CHECK(ctx);
     return 0;
   }
   CUtensorMap tmap;
-  if (int e = make_tmap(ctx, &tmap, io.in, io.in_C, io.w, io.h, io.Nw, net->fp16)) return e;
+  if (int e = make_tmap(ctx, &tmap, io.in, io.in_C, io.w, io.h, io.Nw, L.fp16)) return e;
   size_t smem = (size_t)P.n_stage * TC_ASTAGE + (size_t)P.n_wbuf * L.chunk_bytes + SMEM_SLACK;
   int grid = P.n_tiles < ctx->sm_count ? P.n_tiles : ctx->sm_count;
   int64_t optG = wowsr_opt(ctx, "tc_grid", 0);
   if (optG > 0 && optG < grid) grid = (int)optG;
-  if (net->fp16) {
-    WCUDA(ctx, cudaFuncSetAttribute(conv3x3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
-    conv3x3_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(tmap, P);
-  } else {
-    WCUDA(ctx, cudaFuncSetAttribute(conv3x3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
-    conv3x3_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(tmap, P);
+  if (!ctx->tc_attr_set) {  // per device (one handle per device)
+    WCUDA(ctx, cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+    ctx->tc_attr_set = true;
   }
+  conv3x3_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmap, P);
   WLAUNCH_CHECK(ctx);
   return 0;
 }
@@ -261,7 +261,7 @@ int rrdbnet_batch(wowsr_ctx* ctx, ConvNet* net, const uint8_t* img, long long pi
                   uint8_t* out, long long out_pitch, float* out_f32, long long out_f32_pitch, cudaStream_t st) {
   const int h = wins[0].y1 - wins[0].y0, w = wins[0].x1 - wins[0].x0;
   const size_t px = (size_t)nb * h * w;
-  const bool fp16 = net->fp16;
+  const bool body16 = net->body_fp16, tail16 = net->tail_fp16;
   if (int e = wowsr_ensure(ctx, net->dense0, px * 192 * 2)) return e;
   if (int e = wowsr_ensure(ctx, net->dense1, px * 192 * 2)) return e;
   if (int e = wowsr_ensure(ctx, net->feat, px * 64 * 4)) return e;
@@ -290,10 +290,9 @@ int rrdbnet_batch(wowsr_ctx* ctx, ConvNet* net, const uint8_t* img, long long pi
     F.img = img; F.pitch = pitch; F.cin = 3; F.win_xy = (const int*)net->winxy.p;
     F.Nw = nb; F.h = h; F.w = w; F.weight = net->first_w; F.bias = net->first_b;
     F.f32_a = (float*)net->feat.p; F.f32_b = (float*)net->trunk.p; F.f32_c = (float*)net->rrdb.p;
-    F.out_t = net->dense0.p; F.out_stride = 192; F.in_scale_div = 255.0f;
+    F.out_t = net->dense0.p; F.out_stride = 192; F.out_fp16 = body16; F.in_scale_div = 255.0f;
     dim3 grid((unsigned)((px + 127) / 128), 4);
-    if (fp16) conv_first_kernel<true><<<grid, 128, 0, st>>>(F);
-    else conv_first_kernel<false><<<grid, 128, 0, st>>>(F);
+    conv_first_kernel<<<grid, 128, 0, st>>>(F);
     WLAUNCH_CHECK(ctx);
   }
   WCUDA(ctx, cudaEventRecord(ctx->ev[1], st));
@@ -306,7 +305,7 @@ int rrdbnet_batch(wowsr_ctx* ctx, ConvNet* net, const uint8_t* img, long long pi
         LayerIO io;
         io.in = cur; io.in_C = 192; io.Nw = nb; io.h = h; io.w = w;
         io.act = 1;
-        io.out_t = cur; io.out_stride = 192; io.out_choff = 64 + 32 * k;
+        io.out_t = cur; io.out_stride = 192; io.out_choff = 64 + 32 * k; io.out_fp16 = body16;
         if (int e = run_conv(ctx, net, net->layers[li++], io, st)) return e;
       }
       LayerIO io;
@@ -318,6 +317,8 @@ int rrdbnet_batch(wowsr_ctx* ctx, ConvNet* net, const uint8_t* img, long long pi
         io.out_f32_b = (float*)net->rrdb.p;
       }
       io.out_t = nxt; io.out_stride = 192; io.out_choff = 0;
+      // the last RDB feeds conv_body, which may run in a different operand type (mixed precision)
+      io.out_fp16 = (b == net->num_block - 1 && r == 2) ? tail16 : body16;
       if (int e = run_conv(ctx, net, net->layers[li++], io, st)) return e;
       std::swap(cur, nxt);
     }
@@ -326,25 +327,25 @@ int rrdbnet_batch(wowsr_ctx* ctx, ConvNet* net, const uint8_t* img, long long pi
     LayerIO io;
     io.in = cur; io.in_C = 192; io.Nw = nb; io.h = h; io.w = w;
     io.scale1 = 1.0f; io.res1 = (const float*)net->feat.p;
-    io.out_t = net->up1.p; io.out_stride = 64; io.out_rep = 2;
+    io.out_t = net->up1.p; io.out_stride = 64; io.out_rep = 2; io.out_fp16 = tail16;
     if (int e = run_conv(ctx, net, net->layers[li++], io, st)) return e;
   }
   {  // conv_up1 @2x + lrelu, replicated for conv_up2
     LayerIO io;
     io.in = net->up1.p; io.in_C = 64; io.Nw = nb; io.h = 2 * h; io.w = 2 * w;
-    io.act = 1; io.out_t = net->hra.p; io.out_stride = 64; io.out_rep = 2;
+    io.act = 1; io.out_t = net->hra.p; io.out_stride = 64; io.out_rep = 2; io.out_fp16 = tail16;
     if (int e = run_conv(ctx, net, net->layers[li++], io, st)) return e;
   }
   {  // conv_up2 @4x + lrelu
     LayerIO io;
     io.in = net->hra.p; io.in_C = 64; io.Nw = nb; io.h = 4 * h; io.w = 4 * w;
-    io.act = 1; io.out_t = net->hrb.p; io.out_stride = 64;
+    io.act = 1; io.out_t = net->hrb.p; io.out_stride = 64; io.out_fp16 = tail16;
     if (int e = run_conv(ctx, net, net->layers[li++], io, st)) return e;
   }
   {  // conv_hr + lrelu
     LayerIO io;
     io.in = net->hrb.p; io.in_C = 64; io.Nw = nb; io.h = 4 * h; io.w = 4 * w;
-    io.act = 1; io.out_t = net->hra.p; io.out_stride = 64;
+    io.act = 1; io.out_t = net->hra.p; io.out_stride = 64; io.out_fp16 = tail16;
     if (int e = run_conv(ctx, net, net->layers[li++], io, st)) return e;
   }
   {  // conv_last + quantise + stitch
@@ -378,7 +379,8 @@ extern "C" int wowsr_load_rrdbnet(wowsr_ctx* ctx, int32_t num_block, int32_t num
   ConvNet* net = new ConvNet();
   net->kind = 0;
   net->num_block = num_block;
-  net->fp16 = precision == WOWSR_PREC_FP16;
+  net->body_fp16 = precision == WOWSR_PREC_FP16;
+  net->tail_fp16 = precision != WOWSR_PREC_BF16;
   int t = 0;
   int e = upload_first(ctx, net, tensors[0], tensors[1], 3, 64);
   t = 2;
@@ -386,12 +388,12 @@ extern "C" int wowsr_load_rrdbnet(wowsr_ctx* ctx, int32_t num_block, int32_t num
     for (int r = 0; r < 3 && !e; r++)
       for (int k = 0; k < 5 && !e; k++) {
         net->layers.emplace_back();
-        e = upload_layer(ctx, net->layers.back(), tensors[t], tensors[t + 1], 64 + 32 * k, k < 4 ? 32 : 64, net->fp16);
+        e = upload_layer(ctx, net->layers.back(), tensors[t], tensors[t + 1], 64 + 32 * k, k < 4 ? 32 : 64, net->body_fp16);
         t += 2;
       }
   for (int i = 0; i < 5 && !e; i++) {  // conv_body, conv_up1, conv_up2, conv_hr, conv_last
     net->layers.emplace_back();
-    e = upload_layer(ctx, net->layers.back(), tensors[t], tensors[t + 1], 64, i < 4 ? 64 : 3, net->fp16);
+    e = upload_layer(ctx, net->layers.back(), tensors[t], tensors[t + 1], 64, i < 4 ? 64 : 3, net->tail_fp16);
     t += 2;
   }
   if (!e) e = wowsr_ensure(ctx, net->err, 4);
@@ -484,7 +486,7 @@ extern "C" int wowsr_conv3x3_host(wowsr_ctx* ctx, const float* in, int32_t n, in
   DeviceGuard g(ctx->device);
   const bool fp16 = precision == WOWSR_PREC_FP16;
   ConvNet* net = new ConvNet();
-  net->fp16 = fp16;
+  net->body_fp16 = net->tail_fp16 = fp16;
   net->layers.emplace_back();
   int e = upload_layer(ctx, net->layers[0], weight, bias, cin, cout, fp16);
   const size_t px = (size_t)n * h * w;

@@ -34,7 +34,8 @@ constexpr int TC_MAX_WBUF = 4;
 
 constexpr int CF_STACK = 1;    // stack the three ky taps along N
 constexpr int CF_BASEOFF = 2;  // put (start_addr>>7)&7 into the descriptor base-offset field
-constexpr int CF_FP16 = 4;     // fp16 operands instead of bf16
+constexpr int CF_FP16 = 4;     // fp16 operands (input activations + weights) instead of bf16
+constexpr int CF_OUT_FP16 = 8; // the layer writes fp16 activations (the next layer's operand type)
 
 struct WinDev {  // output-resolution window record for the final layer
   int X0, Y0;              // origin of this window's output in the stitched image
@@ -79,7 +80,7 @@ struct ConvParams {
 // fused epilogue for NCH consecutive channels [ch0, ch0+NCH) of one output pixel
 // ---------------------------------------------------------------------------------------------
 
-template <int NCH, bool FP16>
+template <int NCH>
 __device__ __forceinline__ void epilogue_pixel(const ConvParams& P, int n, int y, int x, int ch0, float (&v)[NCH],
                                                const float* __restrict__ bias) {
 #pragma unroll
@@ -138,12 +139,15 @@ __device__ __forceinline__ void epilogue_pixel(const ConvParams& P, int n, int y
   }
   if (P.out_t) {
     uint32_t pk[NCH / 2];
+    if (P.flags & CF_OUT_FP16) {
 #pragma unroll
-    for (int i = 0; i < NCH / 2; i++) {
-      if (FP16) {
+      for (int i = 0; i < NCH / 2; i++) {
         __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
         pk[i] = *reinterpret_cast<uint32_t*>(&hh);
-      } else {
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NCH / 2; i++) {
         __nv_bfloat162 bb = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
         pk[i] = *reinterpret_cast<uint32_t*>(&bb);
       }
@@ -176,7 +180,6 @@ __device__ __forceinline__ void tc_fail(const ConvParams& P, int code) {
   if (P.err_flag) atomicCAS(P.err_flag, 0, code);
 }
 
-template <bool FP16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -253,7 +256,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams P) 
       int stage = 0;
       uint32_t aphase = 0, wcount = 0;
       bool ok = true;
-      const bool stacked = P.flags & CF_STACK, baseoff = P.flags & CF_BASEOFF;
+      const bool stacked = P.flags & CF_STACK;
+      const uint64_t adesc0 = ptx::smem_desc_sw128(a_smem, 1024, 0);
+      const uint64_t bdesc0 = ptx::smem_desc_sw128(w_smem, 1024, 0);
+      const uint32_t idesc1 = P.idesc_base | ((uint32_t)(N >> 3) << 17);
       for (int tile = blockIdx.x, it = 0; tile < P.n_tiles && ok; tile += gridDim.x, it++) {
         const int accbuf = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
@@ -274,37 +280,46 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams P) 
             wb = c;
           }
           ptx::tc_fence_after();
-          const uint32_t wbase = w_smem + wb * P.w_chunk_bytes;
           for (int yy = 0; yy < R + 2; yy++) {
             ok = ptx::mbar_wait(ptx::smem_u32(&ctl->a_full[stage]), aphase);
             if (!ok) { tc_fail(P, 23); break; }
             ptx::tc_fence_after();
-            const uint32_t abase = a_smem + stage * TC_ASTAGE;
             const int jlo = yy < 2 ? 2 - yy : 0;
             const int jhi = R + 1 - yy < 2 ? R + 1 - yy : 2;
-            for (int kx = 0; kx < 3; kx++) {
-              for (int ks = 0; ks < ksteps; ks++) {
-                const uint64_t adesc = ptx::smem_desc_sw128(abase + kx * 128 + ks * 32, 1024, baseoff ? kx : 0);
-                const uint32_t wk = wbase + kx * (3 * N * 128) + ks * 32;
-                const bool first = (c == 0 && kx == 0 && ks == 0);
-                if (stacked) {
-                  int jh = jhi;
-                  if (first && jhi == 2) {  // ky=0 block: first contribution to output row yy
-                    ptx::mma_f16_ss(acc_base + yy * N, adesc, ptx::smem_desc_sw128(wk + 2 * N * 128, 1024, 0),
-                                    P.idesc_base | ((uint32_t)(N >> 3) << 17), 0);
-                    jh = 1;
-                  }
-                  if (jlo <= jh) {
-                    const int ne = (jh - jlo + 1) * N;
-                    ptx::mma_f16_ss(acc_base + (yy - 2 + jlo) * N, adesc, ptx::smem_desc_sw128(wk + jlo * N * 128, 1024, 0),
-                                    P.idesc_base | ((uint32_t)(ne >> 3) << 17), 1);
-                  }
+            // descriptors differ only in the 14-bit start-address field: advance them by adding (bytes >> 4)
+            const uint64_t ad0 = adesc0 + (uint64_t)((stage * TC_ASTAGE) >> 4);
+            const uint64_t bd0 = bdesc0 + (uint64_t)((wb * P.w_chunk_bytes) >> 4);
+            if (stacked) {
+              const uint32_t col = acc_base + (yy - 2 + jlo) * N;
+              const uint32_t idesc = P.idesc_base | ((uint32_t)(((jhi - jlo + 1) * N) >> 3) << 17);
+              const uint64_t bdj = bd0 + (uint64_t)(jlo * N * 8);
+              int k0 = 0;
+              if (c == 0) {  // very first k-step of the tile: the ky=0 block initialises output row yy
+                if (jhi == 2) {
+                  ptx::mma_f16_ss(acc_base + yy * N, ad0, bd0 + (uint64_t)(2 * N * 8), idesc1, 0);
+                  if (jlo <= 1)
+                    ptx::mma_f16_ss(col, ad0, bdj, P.idesc_base | ((uint32_t)(((2 - jlo) * N) >> 3) << 17), 1);
                 } else {
-                  for (int j = jlo; j <= jhi; j++)
-                    ptx::mma_f16_ss(acc_base + (yy - 2 + j) * N, adesc, ptx::smem_desc_sw128(wk + j * N * 128, 1024, 0),
-                                    P.idesc_base | ((uint32_t)(N >> 3) << 17), (first && j == 2) ? 0u : 1u);
+                  ptx::mma_f16_ss(col, ad0, bdj, idesc, 1);
+                }
+                k0 = 1;
+              }
+#pragma unroll
+              for (int kx = 0; kx < 3; kx++) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ks++) {
+                  if (kx * 4 + ks >= k0 && ks < ksteps)
+                    ptx::mma_f16_ss(col, ad0 + (uint64_t)(kx * 8 + ks * 2), bdj + (uint64_t)(kx * 3 * N * 8 + ks * 2), idesc, 1);
                 }
               }
+            } else {
+              for (int kx = 0; kx < 3; kx++)
+                for (int ks = 0; ks < ksteps; ks++) {
+                  const bool first = (c == 0 && kx == 0 && ks == 0);
+                  for (int j = jlo; j <= jhi; j++)
+                    ptx::mma_f16_ss(acc_base + (yy - 2 + j) * N, ad0 + (uint64_t)(kx * 8 + ks * 2),
+                                    bd0 + (uint64_t)(kx * 3 * N * 8 + j * N * 8 + ks * 2), idesc1, (first && j == 2) ? 0u : 1u);
+                }
             }
             ptx::mma_commit(ptx::smem_u32(&ctl->a_empty[stage]));
             if (++stage == P.n_stage) { stage = 0; aphase ^= 1; }
@@ -341,7 +356,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams P) 
               float v[32];
 #pragma unroll
               for (int i = 0; i < 32; i++) v[i] = __uint_as_float(rr[i]);
-              epilogue_pixel<32, FP16>(P, n, y, x, c32 * 32, v, ctl->bias);
+              epilogue_pixel<32>(P, n, y, x, c32 * 32, v, ctl->bias);
             }
           }
         } else {
@@ -352,7 +367,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams P) 
             float v[16];
 #pragma unroll
             for (int i = 0; i < 16; i++) v[i] = __uint_as_float(rr[i]);
-            epilogue_pixel<16, FP16>(P, n, y, x, 0, v, ctl->bias);
+            epilogue_pixel<16>(P, n, y, x, 0, v, ctl->bias);
           }
         }
       }
@@ -370,7 +385,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams P) 
 // CUDA-core direct convolution with identical semantics (bring-up / cross-check)
 // ---------------------------------------------------------------------------------------------
 
-template <int N, bool FP16>
+template <int N>
 __global__ void __launch_bounds__(128)
 conv3x3_simple_kernel(const ConvParams P) {
   __shared__ float s_bias[64];
@@ -396,7 +411,7 @@ conv3x3_simple_kernel(const ConvParams P) {
       const float* wp = P.wsimple + (long long)(ky * 3 + kx) * P.cin * N;
       for (int ci = 0; ci < P.cin; ci++) {
         float a;
-        if (FP16) a = __half2float(*reinterpret_cast<const __half*>(ip + ci));
+        if (P.flags & CF_FP16) a = __half2float(*reinterpret_cast<const __half*>(ip + ci));
         else a = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(ip + ci));
         const float* wr = wp + (long long)ci * N;
 #pragma unroll
@@ -410,13 +425,13 @@ conv3x3_simple_kernel(const ConvParams P) {
       float v[32];
 #pragma unroll
       for (int i = 0; i < 32; i++) v[i] = acc[c32 * 32 + i];
-      epilogue_pixel<32, FP16>(P, n, y, x, c32 * 32, v, s_bias);
+      epilogue_pixel<32>(P, n, y, x, c32 * 32, v, s_bias);
     }
   } else {
     float v[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) v[i] = acc[i];
-    epilogue_pixel<16, FP16>(P, n, y, x, 0, v, s_bias);
+    epilogue_pixel<16>(P, n, y, x, 0, v, s_bias);
   }
 }
 
@@ -439,11 +454,11 @@ struct FirstParams {
   float* f32_c;
   void* out_t;
   int out_stride;
+  int out_fp16;
   float in_scale_div;   // 255 for RRDBNet
   float sub[3];         // per-channel mean subtracted after scaling (EDSR), 0 for RRDBNet
 };
 
-template <bool FP16>
 __global__ void __launch_bounds__(128)
 conv_first_kernel(const FirstParams P) {
   __shared__ float s_w[27 * 64];
@@ -493,7 +508,7 @@ conv_first_kernel(const FirstParams P) {
     uint32_t pk[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-      if (FP16) {
+      if (P.out_fp16) {
         __half2 hh = __floats2half2_rn(acc[2 * i], acc[2 * i + 1]);
         pk[i] = *reinterpret_cast<uint32_t*>(&hh);
       } else {
