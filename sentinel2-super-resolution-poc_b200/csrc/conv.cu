@@ -20,6 +20,7 @@ struct LayerW {
   size_t chunk_bytes = 0;
   bool fp16 = false;  // operand type of this layer (input activations and weights)
   uint8_t* wpack = nullptr;
+  uint8_t* wpack_v = nullptr;  // taps transposed, for vertical tiles
   float* wsimple = nullptr;
   float* bias = nullptr;
 };
@@ -41,6 +42,7 @@ void wowsr_net_free(ConvNet* n) {
   if (!n) return;
   for (auto& l : n->layers) {
     if (l.wpack) cudaFree(l.wpack);
+    if (l.wpack_v) cudaFree(l.wpack_v);
     if (l.wsimple) cudaFree(l.wsimple);
     if (l.bias) cudaFree(l.bias);
   }
@@ -79,22 +81,25 @@ int upload_layer(wowsr_ctx* ctx, LayerW& L, const float* w, const float* b, int 
   L.n_chunks = (cin + 63) / 64;
   const int N = L.N;
   L.chunk_bytes = (size_t)3 * 3 * N * 128;
-  std::vector<uint8_t> pack(L.chunk_bytes * L.n_chunks, 0);
+  std::vector<uint8_t> pack(L.chunk_bytes * L.n_chunks, 0), pack_v(L.chunk_bytes * L.n_chunks, 0);
   std::vector<float> simple((size_t)9 * cin * N, 0.0f);
+  // `a` = tap along the run axis (selected by the shifted A descriptor), `j` = stacked tap along the row
+  // axis (row-axis tap index 2-j).  Horizontal tiles: run axis x, row axis y.  Vertical tiles: swapped.
   for (int c = 0; c < L.n_chunks; c++)
-    for (int kx = 0; kx < 3; kx++)
+    for (int a = 0; a < 3; a++)
       for (int j = 0; j < 3; j++) {
-        const int ky = 2 - j;
+        const int b = 2 - j;
         for (int co = 0; co < cout; co++) {
           const int row = j * N + co;
           for (int ch = 0; ch < 64; ch++) {
             const int ci = c * 64 + ch;
             if (ci >= cin) break;
-            const float v = w[(((size_t)co * cin + ci) * 3 + ky) * 3 + kx];
-            const uint16_t t = to_t(v, fp16);
-            size_t off = (size_t)c * L.chunk_bytes + (size_t)kx * (3 * N * 128) + (size_t)row * 128 +
+            size_t off = (size_t)c * L.chunk_bytes + (size_t)a * (3 * N * 128) + (size_t)row * 128 +
                          (size_t)(((ch >> 3) ^ (row & 7)) << 4) + (size_t)(ch & 7) * 2;
-            memcpy(&pack[off], &t, 2);
+            const uint16_t th = to_t(w[(((size_t)co * cin + ci) * 3 + b) * 3 + a], fp16);  // ky = b, kx = a
+            const uint16_t tv = to_t(w[(((size_t)co * cin + ci) * 3 + a) * 3 + b], fp16);  // ky = a, kx = b
+            memcpy(&pack[off], &th, 2);
+            memcpy(&pack_v[off], &tv, 2);
           }
         }
       }
@@ -107,6 +112,8 @@ int upload_layer(wowsr_ctx* ctx, LayerW& L, const float* w, const float* b, int 
   std::vector<float> bias(64, 0.0f);
   for (int co = 0; co < cout; co++) bias[co] = b ? b[co] : 0.0f;
   WCUDA(ctx, cudaMalloc((void**)&L.wpack, pack.size()));
+  WCUDA(ctx, cudaMalloc((void**)&L.wpack_v, pack_v.size()));
+  WCUDA(ctx, cudaMemcpy(L.wpack_v, pack_v.data(), pack_v.size(), cudaMemcpyHostToDevice));
   WCUDA(ctx, cudaMalloc((void**)&L.wsimple, simple.size() * 4));
   WCUDA(ctx, cudaMalloc((void**)&L.bias, 64 * 4));
   WCUDA(ctx, cudaMemcpy(L.wpack, pack.data(), pack.size(), cudaMemcpyHostToDevice));
@@ -142,11 +149,18 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }
 
 // 4-D map over an NHWC activation buffer: dims (C, W, H, N), box (64 ch, 130 px, 1 row, 1 window)
-int make_tmap(wowsr_ctx* ctx, CUtensorMap* m, const void* base, int C, int W, int H, int Nw, bool fp16) {
+// `transposed`: dims (C, H, W, N) — the run axis (box of 130) walks y; used by the vertical tiles.
+int make_tmap(wowsr_ctx* ctx, CUtensorMap* m, const void* base, int C, int W, int H, int Nw, bool fp16, bool transposed) {
   auto enc = get_encode();
   if (!enc) return wowsr_fail(ctx, WOWSR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Nw};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * W, (cuuint64_t)C * 2 * W * H};
+  if (transposed) {
+    dims[1] = (cuuint64_t)H;
+    dims[2] = (cuuint64_t)W;
+    strides[0] = (cuuint64_t)C * 2 * W;
+    strides[1] = (cuuint64_t)C * 2;
+  }
   cuuint32_t box[4] = {64, (cuuint32_t)TC_AROWS, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base),
@@ -230,17 +244,53 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
     WLAUNCH_CHECK(ctx);
     return 0;
   }
-  CUtensorMap tmap;
-  if (int e = make_tmap(ctx, &tmap, io.in, io.in_C, io.w, io.h, io.Nw, L.fp16)) return e;
-  size_t smem = (size_t)P.n_stage * TC_ASTAGE + (size_t)P.n_wbuf * L.chunk_bytes + SMEM_SLACK;
-  int grid = P.n_tiles < ctx->sm_count ? P.n_tiles : ctx->sm_count;
+  CUtensorMap tmap, tmap_v;
+  if (int e = make_tmap(ctx, &tmap, io.in, io.in_C, io.w, io.h, io.Nw, L.fp16, false)) return e;
+  tmap_v = tmap;
+  // Remainder strip (w not a multiple of 128): cover it with vertical runs when that wastes fewer MMA rows.
+  const int wm = io.w / TC_RUN * TC_RUN, rem = io.w - wm;
+  int max_grid = ctx->sm_count;
   int64_t optG = wowsr_opt(ctx, "tc_grid", 0);
-  if (optG > 0 && optG < grid) grid = (int)optG;
+  if (optG > 0 && optG < max_grid) max_grid = (int)optG;
+  bool use_v = false;
+  if (rem > 0 && !wowsr_opt(ctx, "tc_no_strip", 0)) {
+    const int v_runs = (io.h + TC_RUN - 1) / TC_RUN, v_rows = (rem + R - 1) / R;
+    const double eff_h = rem / (double)TC_RUN;
+    const double eff_v = (io.h / (double)(v_runs * TC_RUN)) * (rem / (double)(v_rows * R));
+    if (eff_v > eff_h && max_grid >= 2 && make_tmap(ctx, &tmap_v, io.in, io.in_C, io.w, io.h, io.Nw, L.fp16, true) == 0) {
+      use_v = true;
+      P.strip_x0 = wm;
+      P.v_runs = v_runs;
+      P.v_rows = v_rows;
+      P.n_tiles_v = v_runs * v_rows * io.Nw;
+      P.tiles_x = wm / TC_RUN;
+      P.n_tiles = P.tiles_x * P.tiles_y * io.Nw;
+      P.wpack_v = L.wpack_v;
+    }
+  }
+  int grid = P.n_tiles + P.n_tiles_v < max_grid ? P.n_tiles + P.n_tiles_v : max_grid;
+  P.grid_h = grid;
+  if (use_v) {
+    if (P.n_tiles == 0) {
+      P.grid_h = 0;
+    } else {
+      // split the CTAs between the two orientations so that both finish together (tiles cost the same)
+      int best = 1;
+      long long best_t = -1;
+      for (int gv = 1; gv < grid; gv++) {
+        long long th = (P.n_tiles + (grid - gv) - 1) / (grid - gv), tv = (P.n_tiles_v + gv - 1) / gv;
+        long long t = th > tv ? th : tv;
+        if (best_t < 0 || t < best_t) { best_t = t; best = gv; }
+      }
+      P.grid_h = grid - best;
+    }
+  }
+  size_t smem = (size_t)P.n_stage * TC_ASTAGE + (size_t)P.n_wbuf * L.chunk_bytes + SMEM_SLACK;
   if (!ctx->tc_attr_set) {  // per device (one handle per device)
     WCUDA(ctx, cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
     ctx->tc_attr_set = true;
   }
-  conv3x3_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmap, P);
+  conv3x3_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmap, tmap_v, P);
   WLAUNCH_CHECK(ctx);
   return 0;
 }

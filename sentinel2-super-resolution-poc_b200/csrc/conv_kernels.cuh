@@ -46,12 +46,14 @@ struct ConvParams {
   int Nw, h, w;       // windows in the batch, layer resolution
   int cin, n_chunks;  // input channels (multiple of 16), 64-channel chunks
   int N, cout;        // padded / real output channels
-  int R, tiles_x, tiles_y, n_tiles;
+  int R, tiles_x, tiles_y, n_tiles;  // horizontal tiles: runs per row, row blocks, total
+  int grid_h, strip_x0, v_runs, v_rows, n_tiles_v;  // vertical tiles of the remainder strip (n_tiles_v = 0: none)
   int flags;
   uint32_t idesc_base;  // instruction descriptor with N = 0
   int w_resident, n_wbuf, n_stage;
   uint32_t w_chunk_bytes;
   const uint8_t* wpack;  // [chunk][kx][j=2-ky][co][64ch] K-major, 128B-swizzled image of smem
+  const uint8_t* wpack_v;  // same with the 3x3 taps transposed (vertical tiles)
   const float* wsimple;  // [ky][kx][ci][N] operand-rounded weights for the simple kernel
   const float* bias;     // [N]
   const void* in;        // simple kernel: input activations (T), pixel stride in_stride, offset 0
@@ -180,10 +182,36 @@ __device__ __forceinline__ void tc_fail(const ConvParams& P, int code) {
   if (P.err_flag) atomicCAS(P.err_flag, 0, code);
 }
 
+// Tile geometry.  CTAs [0, grid_h) walk "horizontal" tiles (runs of 128 pixels along x, R image rows per
+// tile) over x in [0, strip_x0); CTAs [grid_h, gridDim.x) walk "vertical" tiles (runs of 128 pixels along
+// y, R image columns per tile) over the remainder strip x in [strip_x0, w).  A vertical tile is the same
+// computation on the transposed image: its tensor map swaps the x/y strides and its weights are packed
+// with the 3x3 taps transposed.  Without a strip every CTA is horizontal and covers the whole width.
+struct TileCoord {
+  int n, u0, v0;  // window, run-axis origin, row-axis origin
+};
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& P, bool vert, int tile) {
+  TileCoord t;
+  const int runs = vert ? P.v_runs : P.tiles_x, rows = vert ? P.v_rows : P.tiles_y;
+  const int per_win = runs * rows;
+  t.n = tile / per_win;
+  const int tr = tile - t.n * per_win;
+  const int vb = tr / runs, ur = tr - vb * runs;
+  t.u0 = ur * TC_RUN;
+  t.v0 = (vert ? P.strip_x0 : 0) + vb * P.R;
+  return t;
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams P) {
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__ CUtensorMap tmap_v, const ConvParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool vert = (int)blockIdx.x >= P.grid_h;
+  const CUtensorMap& tmap = vert ? tmap_v : tmap_h;
+  const uint8_t* wpack = vert ? P.wpack_v : P.wpack;
+  const int tile0 = vert ? (int)blockIdx.x - P.grid_h : (int)blockIdx.x;
+  const int tile_step = vert ? (int)gridDim.x - P.grid_h : P.grid_h;
+  const int tile_end = vert ? P.n_tiles_v : P.n_tiles;
   const uint32_t smem_base = (ptx::smem_u32(smem) + 1023u) & ~1023u;
   const uint32_t a_smem = smem_base;
   const uint32_t w_smem = a_smem + P.n_stage * TC_ASTAGE;
@@ -193,7 +221,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams P) 
   const uint32_t tmem_cols = 2u * R * N <= 32 ? 32u : (2u * R * N <= 64 ? 64u : (2u * R * N <= 128 ? 128u : (2u * R * N <= 256 ? 256u : 512u)));
 
   if (threadIdx.x == 0) {
-    ptx::prefetch_tmap(&tmap);
+    ptx::prefetch_tmap(&tmap);  // this CTA's orientation
     for (int i = 0; i < P.n_stage; i++) {
       ptx::mbar_init(ptx::smem_u32(&ctl->a_full[i]), 1);
       ptx::mbar_init(ptx::smem_u32(&ctl->a_empty[i]), 1);
@@ -216,83 +244,89 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams P) 
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = ctl->tmem_base;
-  const int tiles_per_win = P.tiles_x * P.tiles_y;
+  const uint32_t tmem_base = __shfl_sync(0xFFFFFFFFu, ctl->tmem_base, 0);
 
+  // Both single-thread roles run their loops on the WHOLE warp (warp-uniform control flow and values, so
+  // descriptors and barrier addresses live in uniform registers) and predicate only the issuing
+  // instructions on one elected lane.  A lane-0-only loop makes nvcc wrap every tcgen05.mma in an
+  // elect/R2UR broadcast loop, which costs more than the MMA itself.
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t aphase = 0, wcount = 0;
-      bool ok = true;
-      for (int tile = blockIdx.x, it = 0; tile < P.n_tiles && ok; tile += gridDim.x, it++) {
-        const int n = tile / tiles_per_win, tr = tile - n * tiles_per_win;
-        const int yb = tr / P.tiles_x, xr = tr - yb * P.tiles_x;
-        const int x0 = xr * TC_RUN, y0 = yb * R;
-        for (int c = 0; c < P.n_chunks && ok; c++) {
-          if (!(P.w_resident && it > 0)) {
-            const uint32_t b = wcount % P.n_wbuf, use = wcount / P.n_wbuf;
-            if (!P.w_resident) ok = ptx::mbar_wait(ptx::smem_u32(&ctl->w_empty[b]), (use & 1) ^ 1);
-            if (!ok) { tc_fail(P, 11); break; }
+    const bool leader = ptx::elect_one();
+    int stage = 0;
+    uint32_t aphase = 0, wcount = 0;
+    bool ok = true;
+    for (int tile = tile0, it = 0; tile < tile_end && ok; tile += tile_step, it++) {
+      const TileCoord tc = decode_tile(P, vert, tile);
+      for (int c = 0; c < P.n_chunks && ok; c++) {
+        if (!(P.w_resident && it > 0)) {
+          const uint32_t b = wcount % P.n_wbuf, use = wcount / P.n_wbuf;
+          if (!P.w_resident) ok = __all_sync(0xFFFFFFFFu, ptx::mbar_wait(ptx::smem_u32(&ctl->w_empty[b]), (use & 1) ^ 1));
+          if (!ok) { tc_fail(P, 11); break; }
+          if (leader) {
             ptx::mbar_arrive_expect_tx(ptx::smem_u32(&ctl->w_full[b]), P.w_chunk_bytes);
-            ptx::bulk_load(w_smem + b * P.w_chunk_bytes, P.wpack + (size_t)c * P.w_chunk_bytes, P.w_chunk_bytes,
+            ptx::bulk_load(w_smem + b * P.w_chunk_bytes, wpack + (size_t)c * P.w_chunk_bytes, P.w_chunk_bytes,
                            ptx::smem_u32(&ctl->w_full[b]));
-            wcount++;
           }
-          for (int yy = 0; yy < R + 2; yy++) {
-            ok = ptx::mbar_wait(ptx::smem_u32(&ctl->a_empty[stage]), aphase ^ 1);
-            if (!ok) { tc_fail(P, 12); break; }
+          wcount++;
+        }
+        for (int yy = 0; yy < R + 2; yy++) {
+          ok = __all_sync(0xFFFFFFFFu, ptx::mbar_wait(ptx::smem_u32(&ctl->a_empty[stage]), aphase ^ 1));
+          if (!ok) { tc_fail(P, 12); break; }
+          if (leader) {
             ptx::mbar_arrive_expect_tx(ptx::smem_u32(&ctl->a_full[stage]), TC_ABYTES);
-            ptx::tma_load_4d(a_smem + stage * TC_ASTAGE, &tmap, ptx::smem_u32(&ctl->a_full[stage]), c * 64, x0 - 1,
-                             y0 - 1 + yy, n);
-            if (++stage == P.n_stage) { stage = 0; aphase ^= 1; }
+            ptx::tma_load_4d(a_smem + stage * TC_ASTAGE, &tmap, ptx::smem_u32(&ctl->a_full[stage]), c * 64, tc.u0 - 1,
+                             tc.v0 - 1 + yy, tc.n);
           }
+          if (++stage == P.n_stage) { stage = 0; aphase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t aphase = 0, wcount = 0;
-      bool ok = true;
-      const bool stacked = P.flags & CF_STACK;
-      const uint64_t adesc0 = ptx::smem_desc_sw128(a_smem, 1024, 0);
-      const uint64_t bdesc0 = ptx::smem_desc_sw128(w_smem, 1024, 0);
-      const uint32_t idesc1 = P.idesc_base | ((uint32_t)(N >> 3) << 17);
-      for (int tile = blockIdx.x, it = 0; tile < P.n_tiles && ok; tile += gridDim.x, it++) {
-        const int accbuf = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        ok = ptx::mbar_wait(ptx::smem_u32(&ctl->t_empty[accbuf]), acc_phase ^ 1);
-        if (!ok) { tc_fail(P, 21); break; }
+    // ===================== MMA issuer =====================
+    const bool leader = ptx::elect_one();
+    int stage = 0;
+    uint32_t aphase = 0, wcount = 0;
+    bool ok = true;
+    const bool stacked = P.flags & CF_STACK;
+    const uint64_t adesc0 = ptx::smem_desc_sw128(a_smem, 1024, 0);
+    const uint64_t bdesc0 = ptx::smem_desc_sw128(w_smem, 1024, 0);
+    const uint32_t idesc1 = P.idesc_base | ((uint32_t)(N >> 3) << 17);
+    for (int tile = tile0, it = 0; tile < tile_end && ok; tile += tile_step, it++) {
+      const int accbuf = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      ok = __all_sync(0xFFFFFFFFu, ptx::mbar_wait(ptx::smem_u32(&ctl->t_empty[accbuf]), acc_phase ^ 1));
+      if (!ok) { tc_fail(P, 21); break; }
+      ptx::tc_fence_after();
+      const uint32_t acc_base = tmem_base + accbuf * R * N;
+      for (int c = 0; c < P.n_chunks && ok; c++) {
+        int ksteps = (P.cin - c * 64) / 16;
+        if (ksteps > 4) ksteps = 4;
+        uint32_t wb;
+        if (!(P.w_resident && it > 0)) {
+          wb = wcount % P.n_wbuf;
+          ok = __all_sync(0xFFFFFFFFu, ptx::mbar_wait(ptx::smem_u32(&ctl->w_full[wb]), (wcount / P.n_wbuf) & 1));
+          if (!ok) { tc_fail(P, 22); break; }
+          wcount++;
+        } else {
+          wb = c;
+        }
         ptx::tc_fence_after();
-        const uint32_t acc_base = tmem_base + accbuf * R * N;
-        for (int c = 0; c < P.n_chunks && ok; c++) {
-          int ksteps = (P.cin - c * 64) / 16;
-          if (ksteps > 4) ksteps = 4;
-          uint32_t wb;
-          if (!(P.w_resident && it > 0)) {
-            wb = wcount % P.n_wbuf;
-            ok = ptx::mbar_wait(ptx::smem_u32(&ctl->w_full[wb]), (wcount / P.n_wbuf) & 1);
-            if (!ok) { tc_fail(P, 22); break; }
-            wcount++;
-          } else {
-            wb = c;
-          }
+        const uint64_t bd0 = bdesc0 + (uint64_t)((wb * P.w_chunk_bytes) >> 4);
+        for (int yy = 0; yy < R + 2; yy++) {
+          ok = __all_sync(0xFFFFFFFFu, ptx::mbar_wait(ptx::smem_u32(&ctl->a_full[stage]), aphase));
+          if (!ok) { tc_fail(P, 23); break; }
           ptx::tc_fence_after();
-          for (int yy = 0; yy < R + 2; yy++) {
-            ok = ptx::mbar_wait(ptx::smem_u32(&ctl->a_full[stage]), aphase);
-            if (!ok) { tc_fail(P, 23); break; }
-            ptx::tc_fence_after();
-            const int jlo = yy < 2 ? 2 - yy : 0;
-            const int jhi = R + 1 - yy < 2 ? R + 1 - yy : 2;
-            // descriptors differ only in the 14-bit start-address field: advance them by adding (bytes >> 4)
-            const uint64_t ad0 = adesc0 + (uint64_t)((stage * TC_ASTAGE) >> 4);
-            const uint64_t bd0 = bdesc0 + (uint64_t)((wb * P.w_chunk_bytes) >> 4);
+          const int jlo = yy < 2 ? 2 - yy : 0;
+          const int jhi = R + 1 - yy < 2 ? R + 1 - yy : 2;
+          // descriptors differ only in the 14-bit start-address field: advance them by adding (bytes >> 4)
+          const uint64_t ad0 = adesc0 + (uint64_t)((stage * TC_ASTAGE) >> 4);
+          const uint32_t col = acc_base + (yy - 2 + jlo) * N;
+          const uint32_t idesc = P.idesc_base | ((uint32_t)(((jhi - jlo + 1) * N) >> 3) << 17);
+          const uint64_t bdj = bd0 + (uint64_t)(jlo * N * 8);
+          const uint32_t a_empty_bar = ptx::smem_u32(&ctl->a_empty[stage]);
+          if (leader) {
             if (stacked) {
-              const uint32_t col = acc_base + (yy - 2 + jlo) * N;
-              const uint32_t idesc = P.idesc_base | ((uint32_t)(((jhi - jlo + 1) * N) >> 3) << 17);
-              const uint64_t bdj = bd0 + (uint64_t)(jlo * N * 8);
               int k0 = 0;
               if (c == 0) {  // very first k-step of the tile: the ky=0 block initialises output row yy
                 if (jhi == 2) {
@@ -321,32 +355,35 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams P) 
                                     bd0 + (uint64_t)(kx * 3 * N * 8 + j * N * 8 + ks * 2), idesc1, (first && j == 2) ? 0u : 1u);
                 }
             }
-            ptx::mma_commit(ptx::smem_u32(&ctl->a_empty[stage]));
-            if (++stage == P.n_stage) { stage = 0; aphase ^= 1; }
+            ptx::mma_commit(a_empty_bar);
           }
-          if (!P.w_resident) ptx::mma_commit(ptx::smem_u32(&ctl->w_empty[wb]));
+          __syncwarp();
+          if (++stage == P.n_stage) { stage = 0; aphase ^= 1; }
         }
-        ptx::mma_commit(ptx::smem_u32(&ctl->t_full[accbuf]));
+        if (!P.w_resident && leader) ptx::mma_commit(ptx::smem_u32(&ctl->w_empty[wb]));
       }
+      if (leader) ptx::mma_commit(ptx::smem_u32(&ctl->t_full[accbuf]));
+      __syncwarp();
     }
   } else {
     // ===================== epilogue warps (TMEM -> registers -> global) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     bool ok = true;
-    for (int tile = blockIdx.x, it = 0; tile < P.n_tiles && ok; tile += gridDim.x, it++) {
-      const int n = tile / tiles_per_win, tr = tile - n * tiles_per_win;
-      const int yb = tr / P.tiles_x, xr = tr - yb * P.tiles_x;
-      const int x = xr * TC_RUN + q * 32 + lane, y0 = yb * R;
+    const int u_lim = vert ? P.h : P.w, v_lim = vert ? P.w : P.h;
+    for (int tile = tile0, it = 0; tile < tile_end && ok; tile += tile_step, it++) {
+      const TileCoord tc = decode_tile(P, vert, tile);
+      const int n = tc.n, u = tc.u0 + q * 32 + lane;
       const int accbuf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       ok = ptx::mbar_wait(ptx::smem_u32(&ctl->t_full[accbuf]), acc_phase);
       if (!ok) { tc_fail(P, 31); break; }
       ptx::tc_fence_after();
       for (int r = 0; r < R; r++) {
-        const int y = y0 + r;
-        if (y >= P.h) break;
+        const int v = tc.v0 + r;
+        if (v >= v_lim) break;
+        const int y = vert ? u : v, x = vert ? v : u;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + accbuf * R * N + r * N;
-        const bool valid = x < P.w;
+        const bool valid = u < u_lim;
         if (N >= 32) {
           for (int c32 = 0; c32 < N / 32; c32++) {
             uint32_t rr[32];

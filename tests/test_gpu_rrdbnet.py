@@ -28,7 +28,7 @@ def _metrics(got_u8, ref_u8):
 
 @pytest.mark.parametrize("cin,cout,act,prec", [(64, 32, 1, "bf16"), (96, 32, 1, "bf16"), (128, 32, 0, "fp16"), (160, 32, 1, "bf16"),
                                                (192, 64, 0, "bf16"), (64, 64, 1, "fp16"), (64, 3, 0, "bf16")])
-@pytest.mark.parametrize("shape", [(2, 11, 150), (1, 40, 276)])
+@pytest.mark.parametrize("shape", [(2, 11, 150), (1, 40, 276), (2, 300, 148), (1, 130, 20)])
 def test_conv3x3_tensor_core_vs_torch(ws, handle, cin, cout, act, prec, shape):
     """One layer: operands rounded to bf16/fp16, fp32 accumulate -> must match an fp64 conv of the rounded
     operands to fp32-accumulation accuracy; also equals the CUDA-core kernel."""
@@ -83,7 +83,8 @@ def test_rrdbnet_small_untiled_and_tiled(ws, handle, weights, prec):
         sd = R.calibrate_conv_last(sd, blocks)
     handle.load_rrdbnet(_tensors(sd, blocks), blocks, precision=prec)
     rng = np.random.default_rng(0)
-    for (shape, tile) in (((50, 70), 256), ((50, 70), 16), ((37, 141), 256)):
+    # (150, 276) and (276, 150): remainder strip covered by vertical-run tiles (HR layers too: 1104 = 8*128+80)
+    for (shape, tile) in (((50, 70), 256), ((50, 70), 16), ((37, 141), 256), ((150, 276), 256), ((276, 150), 256)):
         img = rng.integers(0, 256, shape + (3,), dtype=np.uint8)
         u8, f = handle.enhance_host(img, tile, want_float=True)
         ref_f = R.enhance_float(sd, img, blocks, tile)
