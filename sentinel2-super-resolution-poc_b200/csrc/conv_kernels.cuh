@@ -24,7 +24,10 @@
 
 #include "ptx.cuh"
 
-constexpr int TC_THREADS = 192;       // warp0 TMA producer, warp1 MMA issuer, warps2-5 epilogue
+constexpr int TC_THREADS = 192;       // warps 0-3 epilogue (one per SM sub-partition), warp 4 TMA producer, warp 5 MMA issuer
+// The issuing warps get the HIGHEST warp ids: the sub-partition arbiter favours higher ids, and an MMA issuer
+// that shares a sub-partition with a busy epilogue warp of higher id gets starved (measured).
+constexpr int TC_WARP_TMA = 4, TC_WARP_MMA = 5;
 constexpr int TC_RUN = 128;           // output pixels per M-run
 constexpr int TC_AROWS = TC_RUN + 2;  // input pixels per row stage
 constexpr int TC_ABYTES = TC_AROWS * 128;
@@ -220,7 +223,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
   const int R = P.R, N = P.N;
   const uint32_t tmem_cols = 2u * R * N <= 32 ? 32u : (2u * R * N <= 64 ? 64u : (2u * R * N <= 128 ? 128u : (2u * R * N <= 256 ? 256u : 512u)));
 
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 128) {
     ptx::prefetch_tmap(&tmap);  // this CTA's orientation
     for (int i = 0; i < P.n_stage; i++) {
       ptx::mbar_init(ptx::smem_u32(&ctl->a_full[i]), 1);
@@ -236,11 +239,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == TC_WARP_MMA) {
     ptx::tmem_alloc(ptx::smem_u32(&ctl->tmem_base), tmem_cols);
     ptx::tmem_relinquish();
   }
-  if (threadIdx.x >= 64 && threadIdx.x < 128) ctl->bias[threadIdx.x - 64] = (int)(threadIdx.x - 64) < N ? P.bias[threadIdx.x - 64] : 0.0f;
+  if (threadIdx.x < 64) ctl->bias[threadIdx.x] = (int)threadIdx.x < N ? P.bias[threadIdx.x] : 0.0f;
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -250,7 +253,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
   // descriptors and barrier addresses live in uniform registers) and predicate only the issuing
   // instructions on one elected lane.  A lane-0-only loop makes nvcc wrap every tcgen05.mma in an
   // elect/R2UR broadcast loop, which costs more than the MMA itself.
-  if (warp == 0) {
+  if (warp == TC_WARP_TMA) {
     // ===================== TMA producer =====================
     const bool leader = ptx::elect_one();
     int stage = 0;
@@ -282,17 +285,29 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == TC_WARP_MMA) {
     // ===================== MMA issuer =====================
+    // Per stage (one input row x one 64-channel chunk): 3 run-axis taps x ksteps K-steps, each ONE
+    // tcgen05.mma whose N stacks the row-axis taps (N, 2N or 3N columns: tile-edge rows feed fewer output
+    // rows).  The wait for the NEXT stage's TMA data is issued between the MMAs of the current stage so its
+    // latency hides behind queued tensor work.
     const bool leader = ptx::elect_one();
+    const uint32_t desc_hi = (uint32_t)(ptx::smem_desc_sw128(0, 1024, 0) >> 32);
+    const uint32_t a_lo0 = ((a_smem >> 4) & 0x3FFFu) | (1u << 16);
+    const uint32_t b_lo0 = ((w_smem >> 4) & 0x3FFFu) | (1u << 16);
+    const uint32_t idn1 = P.idesc_base | ((uint32_t)(N >> 3) << 17);
+    const uint32_t idn2 = P.idesc_base | ((uint32_t)((2 * N) >> 3) << 17);
+    const uint32_t idn3 = P.idesc_base | ((uint32_t)((3 * N) >> 3) << 17);
+    const uint32_t full0 = ptx::smem_u32(&ctl->a_full[0]), empty0 = ptx::smem_u32(&ctl->a_empty[0]);
+    const int n_my = tile0 < tile_end ? (tile_end - tile0 + tile_step - 1) / tile_step : 0;
     int stage = 0;
     uint32_t aphase = 0, wcount = 0;
     bool ok = true;
-    const bool stacked = P.flags & CF_STACK;
-    const uint64_t adesc0 = ptx::smem_desc_sw128(a_smem, 1024, 0);
-    const uint64_t bdesc0 = ptx::smem_desc_sw128(w_smem, 1024, 0);
-    const uint32_t idesc1 = P.idesc_base | ((uint32_t)(N >> 3) << 17);
-    for (int tile = tile0, it = 0; tile < tile_end && ok; tile += tile_step, it++) {
+    if (n_my > 0) {
+      ok = __all_sync(0xFFFFFFFFu, ptx::mbar_wait(full0, 0));
+      if (!ok) tc_fail(P, 23);
+    }
+    for (int it = 0; it < n_my && ok; it++) {
       const int accbuf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       ok = __all_sync(0xFFFFFFFFu, ptx::mbar_wait(ptx::smem_u32(&ctl->t_empty[accbuf]), acc_phase ^ 1));
@@ -312,53 +327,55 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
           wb = c;
         }
         ptx::tc_fence_after();
-        const uint64_t bd0 = bdesc0 + (uint64_t)((wb * P.w_chunk_bytes) >> 4);
+        const uint32_t b_lo = b_lo0 + ((wb * P.w_chunk_bytes) >> 4);
         for (int yy = 0; yy < R + 2; yy++) {
-          ok = __all_sync(0xFFFFFFFFu, ptx::mbar_wait(ptx::smem_u32(&ctl->a_full[stage]), aphase));
-          if (!ok) { tc_fail(P, 23); break; }
-          ptx::tc_fence_after();
+          const bool last = (yy == R + 1) && (c == P.n_chunks - 1) && (it == n_my - 1);
           const int jlo = yy < 2 ? 2 - yy : 0;
           const int jhi = R + 1 - yy < 2 ? R + 1 - yy : 2;
-          // descriptors differ only in the 14-bit start-address field: advance them by adding (bytes >> 4)
-          const uint64_t ad0 = adesc0 + (uint64_t)((stage * TC_ASTAGE) >> 4);
+          const int nb = jhi - jlo + 1;
+          const uint32_t idesc = nb == 3 ? idn3 : (nb == 2 ? idn2 : idn1);
           const uint32_t col = acc_base + (yy - 2 + jlo) * N;
-          const uint32_t idesc = P.idesc_base | ((uint32_t)(((jhi - jlo + 1) * N) >> 3) << 17);
-          const uint64_t bdj = bd0 + (uint64_t)(jlo * N * 8);
-          const uint32_t a_empty_bar = ptx::smem_u32(&ctl->a_empty[stage]);
+          const uint32_t a_lo = a_lo0 + stage * (TC_ASTAGE >> 4);
+          const uint32_t bj = b_lo + jlo * N * 8;
+          int ns = stage + 1;
+          uint32_t np = aphase;
+          if (ns == P.n_stage) { ns = 0; np ^= 1; }
           if (leader) {
-            if (stacked) {
-              int k0 = 0;
-              if (c == 0) {  // very first k-step of the tile: the ky=0 block initialises output row yy
-                if (jhi == 2) {
-                  ptx::mma_f16_ss(acc_base + yy * N, ad0, bd0 + (uint64_t)(2 * N * 8), idesc1, 0);
-                  if (jlo <= 1)
-                    ptx::mma_f16_ss(col, ad0, bdj, P.idesc_base | ((uint32_t)(((2 - jlo) * N) >> 3) << 17), 1);
-                } else {
-                  ptx::mma_f16_ss(col, ad0, bdj, idesc, 1);
-                }
-                k0 = 1;
+            int k0 = 0;
+            if (c == 0) {  // very first k-step of the tile: the row-tap-0 block initialises output row yy
+              if (jhi == 2) {
+                ptx::mma_f16_ss2(acc_base + yy * N, a_lo, b_lo + 2 * N * 8, desc_hi, idn1, 0);
+                if (jlo <= 1) ptx::mma_f16_ss2(col, a_lo, bj, desc_hi, jlo == 0 ? idn2 : idn1, 1);
+              } else {
+                ptx::mma_f16_ss2(col, a_lo, bj, desc_hi, idesc, 1);
               }
-#pragma unroll
-              for (int kx = 0; kx < 3; kx++) {
-#pragma unroll
-                for (int ks = 0; ks < 4; ks++) {
-                  if (kx * 4 + ks >= k0 && ks < ksteps)
-                    ptx::mma_f16_ss(col, ad0 + (uint64_t)(kx * 8 + ks * 2), bdj + (uint64_t)(kx * 3 * N * 8 + ks * 2), idesc, 1);
-                }
-              }
-            } else {
-              for (int kx = 0; kx < 3; kx++)
-                for (int ks = 0; ks < ksteps; ks++) {
-                  const bool first = (c == 0 && kx == 0 && ks == 0);
-                  for (int j = jlo; j <= jhi; j++)
-                    ptx::mma_f16_ss(acc_base + (yy - 2 + j) * N, ad0 + (uint64_t)(kx * 8 + ks * 2),
-                                    bd0 + (uint64_t)(kx * 3 * N * 8 + j * N * 8 + ks * 2), idesc1, (first && j == 2) ? 0u : 1u);
-                }
+              k0 = 1;
             }
-            ptx::mma_commit(a_empty_bar);
+#pragma unroll
+            for (int kx = 0; kx < 2; kx++) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ks++) {
+                if (kx * 4 + ks >= k0 && ks < ksteps)
+                  ptx::mma_f16_ss2(col, a_lo + (kx * 8 + ks * 2), bj + (kx * 3 * N * 8 + ks * 2), desc_hi, idesc, 1);
+              }
+            }
+          }
+          if (!last) {  // prefetch-wait: the next stage's operands (overlaps the MMAs queued above)
+            ok = __all_sync(0xFFFFFFFFu, ptx::mbar_wait(full0 + 8 * ns, np));
+            if (!ok) { tc_fail(P, 23); break; }
+            ptx::tc_fence_after();
+          }
+          if (leader) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ks++) {
+              if (ks < ksteps)
+                ptx::mma_f16_ss2(col, a_lo + (2 * 8 + ks * 2), bj + (2 * 3 * N * 8 + ks * 2), desc_hi, idesc, 1);
+            }
+            ptx::mma_commit(empty0 + 8 * stage);
           }
           __syncwarp();
-          if (++stage == P.n_stage) { stage = 0; aphase ^= 1; }
+          stage = ns;
+          aphase = np;
         }
         if (!P.w_resident && leader) ptx::mma_commit(ptx::smem_u32(&ctl->w_empty[wb]));
       }
@@ -367,7 +384,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
     }
   } else {
     // ===================== epilogue warps (TMEM -> registers -> global) =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp;  // warps 0-3: TMEM lane quarter == warp id
     bool ok = true;
     const int u_lim = vert ? P.h : P.w, v_lim = vert ? P.w : P.h;
     for (int tile = tile0, it = 0; tile < tile_end && ok; tile += tile_step, it++) {
@@ -415,7 +432,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, tmem_cols);
+  if (warp == TC_WARP_MMA) ptx::tmem_dealloc(tmem_base, tmem_cols);
 }
 
 // ---------------------------------------------------------------------------------------------

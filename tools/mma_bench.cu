@@ -1,0 +1,110 @@
+// Microbenchmark: sustained tcgen05.mma (kind::f16, M=128, cta_group::1, SS) issue rate for the operand
+// patterns the conv kernel uses.  One CTA per SM, operands are whatever is in shared memory.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I sentinel2-super-resolution-poc_b200/csrc tools/mma_bench.cu -o build/mma_bench
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "ptx.cuh"
+
+struct Cfg {
+  int n;         // MMA N
+  int shift;     // 0: A always 1024-aligned; 1: A start cycles +0/+128/+256 B (the kx taps)
+  int acc_mode;  // 0: one accumulator block; 1: sliding window over 8 blocks like the stacked conv
+  int kmode;     // 0: 4 K-steps walk +32 B inside the swizzled row (conv); 1: every MMA uses a fresh 1 KB-aligned A tile
+  int iters;     // MMAs per measurement
+};
+
+__global__ void __launch_bounds__(128, 1) mma_bench_kernel(Cfg c, unsigned long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const uint32_t base = (ptx::smem_u32(smem) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;  // 1.0 (fp16)
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(ptx::smem_u32(&bar), 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0) {
+    ptx::tmem_alloc(ptx::smem_u32(&tmem_slot), 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (warp == 0) {
+    const bool leader = ptx::elect_one();
+    const uint32_t a_smem = base, b_smem = base + 128 * 1024;  // A region 128 KB, B region 64 KB
+    const uint64_t ad = ptx::smem_desc_sw128(a_smem, 1024, 0), bd = ptx::smem_desc_sw128(b_smem, 1024, 0);
+    const uint32_t idesc = make_idesc_f16(128, c.n, true);
+    long long t0 = 0, t1 = 0;
+    for (int rep = 0; rep < 3; rep++) {
+      __syncwarp();
+      t0 = clock64();
+      if (leader) {
+        int stage = 0, blk = 0;
+        for (int i = 0; i < c.iters; i += 12) {
+          const uint32_t col = c.acc_mode ? (uint32_t)((blk % 6) * 32) : 0u;
+#pragma unroll
+          for (int kx = 0; kx < 3; kx++)
+#pragma unroll
+            for (int ks = 0; ks < 4; ks++) {
+              uint64_t a = ad + (uint64_t)(stage * 17408 >> 4);
+              if (c.kmode == 0) a += (uint64_t)((c.shift ? kx * 8 : 0) + ks * 2);
+              else a += (uint64_t)(((kx * 4 + ks) * 1024) >> 4);
+              const uint64_t b = bd + (uint64_t)(((kx * 8192) >> 4) + ks * 2);
+              ptx::mma_f16_ss(tmem + col, a, b, idesc, 1);
+            }
+          stage = (stage + 1) % 6;
+          blk++;
+        }
+        ptx::mma_commit(ptx::smem_u32(&bar));
+      }
+      __syncwarp();
+      ptx::mbar_wait(ptx::smem_u32(&bar), rep & 1);
+      t1 = clock64();
+    }
+    if (leader) out[blockIdx.x] = (unsigned long long)(t1 - t0);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem, 512);
+}
+
+int main() {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  unsigned long long* d;
+  cudaMalloc(&d, sms * 8);
+  const int smem = 200 * 1024 + 2048;
+  cudaFuncSetAttribute(mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int iters = 12 * 2000;
+  printf("%-6s %-6s %-8s %-6s %-12s %-10s %-8s\n", "N", "shift", "acc", "kmode", "cyc/MMA", "ideal", "eff");
+  for (int grid : {1, sms})
+    for (int n : {32, 48, 64, 96, 128, 192, 256})
+      for (int shift : {0, 1})
+        for (int acc : {0, 1})
+          for (int kmode : {0, 1}) {
+            if (kmode == 1 && shift == 1) continue;
+            if (acc == 1 && n > 96 + 0 && n != 192) continue;
+            Cfg c{n, shift, acc, kmode, iters};
+            mma_bench_kernel<<<grid, 128, smem>>>(c, d);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) {
+              printf("N=%d failed: %s\n", n, cudaGetErrorString(e));
+              return 1;
+            }
+            std::vector<unsigned long long> h(grid);
+            cudaMemcpy(h.data(), d, grid * 8, cudaMemcpyDeviceToHost);
+            double avg = 0;
+            for (auto v : h) avg += (double)v;
+            avg /= grid;
+            double per = avg / iters, ideal = n / 2.0;
+            printf("%-6d %-6d %-8d %-6d %-12.1f %-10.1f %-8.2f grid=%d\n", n, shift, acc, kmode, per, ideal, ideal / per, grid);
+          }
+  return 0;
+}
