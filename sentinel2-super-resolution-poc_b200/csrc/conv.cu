@@ -73,7 +73,7 @@ int pad_n(int cout) { return cout <= 16 ? 16 : (cout <= 32 ? 32 : 64); }
 
 // weight OIHW fp32 -> (a) smem image for the tensor-core kernel, (b) [ky][kx][ci][N] for the simple one
 int upload_layer(wowsr_ctx* ctx, LayerW& L, const float* w, const float* b, int cin, int cout, bool fp16) {
-  if (cin % 16 != 0 || cout > 64 || cout < 1) return wowsr_fail(ctx, WOWSR_ERR_UNSUPPORTED, "conv %d->%d unsupported", cin, cout);
+  if (cin % 32 != 0 || cout > 64 || cout < 1) return wowsr_fail(ctx, WOWSR_ERR_UNSUPPORTED, "conv %d->%d unsupported (Cin must be a multiple of 32, Cout <= 64)", cin, cout);
   L.cin = cin;
   L.fp16 = fp16;
   L.cout = cout;
@@ -198,10 +198,7 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
   P.Nw = io.Nw; P.h = io.h; P.w = io.w;
   P.cin = L.cin; P.n_chunks = L.n_chunks; P.N = L.N; P.cout = L.cout;
   const int N = L.N;
-  int R = 256 / N;
-  if (R > 8) R = 8;
-  int64_t optR = wowsr_opt(ctx, "tc_rows", 0);
-  if (optR > 0 && optR * N <= 256) R = (int)optR;
+  const int R = N == 64 ? 4 : 8;  // must match conv3x3_tc_kernel<N>
   P.R = R;
   P.tiles_x = (io.w + TC_RUN - 1) / TC_RUN;
   P.tiles_y = (io.h + R - 1) / R;
@@ -287,10 +284,14 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
   }
   size_t smem = (size_t)P.n_stage * TC_ASTAGE + (size_t)P.n_wbuf * L.chunk_bytes + SMEM_SLACK;
   if (!ctx->tc_attr_set) {  // per device (one handle per device)
-    WCUDA(ctx, cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+    WCUDA(ctx, cudaFuncSetAttribute(conv3x3_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+    WCUDA(ctx, cudaFuncSetAttribute(conv3x3_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+    WCUDA(ctx, cudaFuncSetAttribute(conv3x3_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
     ctx->tc_attr_set = true;
   }
-  conv3x3_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmap, tmap_v, P);
+  if (N == 16) conv3x3_tc_kernel<16><<<grid, TC_THREADS, smem, st>>>(tmap, tmap_v, P);
+  else if (N == 32) conv3x3_tc_kernel<32><<<grid, TC_THREADS, smem, st>>>(tmap, tmap_v, P);
+  else conv3x3_tc_kernel<64><<<grid, TC_THREADS, smem, st>>>(tmap, tmap_v, P);
   WLAUNCH_CHECK(ctx);
   return 0;
 }

@@ -205,6 +205,57 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& P, bool vert,
   return t;
 }
 
+
+// NK consecutive K-steps (starting at KS0) of run-axis tap KX of one stage, as ONE asm block: the descriptor
+// bases reach the uniform datapath once and every MMA costs two 64-bit adds (immediates are compile-time:
+// A advances 32 B per K-step and 128 B per tap; B 32 B per K-step and 3*N rows per tap; units of 16 B).
+template <int N, int KX, int KS0, int NK>
+__device__ __forceinline__ void mma_group(uint32_t col, uint64_t a, uint64_t b, uint32_t idesc) {
+  constexpr int A0 = KX * 8 + KS0 * 2, B0 = KX * 3 * N * 8 + KS0 * 2;
+#define WOWSR_MMA_STEP(IA, IB) \
+  "add.u64 ta, %1, %" #IA ";\n\tadd.u64 tb, %2, %" #IB ";\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %3, p;\n\t"
+#define WOWSR_MMA_HEAD "{\n\t.reg .b64 ta, tb;\n\t.reg .pred p;\n\tsetp.eq.u32 p, 0, 0;\n\t"
+  if constexpr (NK == 4) {
+    asm volatile(WOWSR_MMA_HEAD WOWSR_MMA_STEP(4, 5) WOWSR_MMA_STEP(6, 7) WOWSR_MMA_STEP(8, 9) WOWSR_MMA_STEP(10, 11) "}\n" ::"r"(col),
+                 "l"(a), "l"(b), "r"(idesc), "n"(A0), "n"(B0), "n"(A0 + 2), "n"(B0 + 2), "n"(A0 + 4), "n"(B0 + 4), "n"(A0 + 6),
+                 "n"(B0 + 6)
+                 : "memory");
+  } else if constexpr (NK == 3) {
+    asm volatile(WOWSR_MMA_HEAD WOWSR_MMA_STEP(4, 5) WOWSR_MMA_STEP(6, 7) WOWSR_MMA_STEP(8, 9) "}\n" ::"r"(col), "l"(a), "l"(b),
+                 "r"(idesc), "n"(A0), "n"(B0), "n"(A0 + 2), "n"(B0 + 2), "n"(A0 + 4), "n"(B0 + 4)
+                 : "memory");
+  } else if constexpr (NK == 2) {
+    asm volatile(WOWSR_MMA_HEAD WOWSR_MMA_STEP(4, 5) WOWSR_MMA_STEP(6, 7) "}\n" ::"r"(col), "l"(a), "l"(b), "r"(idesc), "n"(A0),
+                 "n"(B0), "n"(A0 + 2), "n"(B0 + 2)
+                 : "memory");
+  } else if constexpr (NK == 1) {
+    asm volatile(WOWSR_MMA_HEAD WOWSR_MMA_STEP(4, 5) "}\n" ::"r"(col), "l"(a), "l"(b), "r"(idesc), "n"(A0), "n"(B0) : "memory");
+  }
+#undef WOWSR_MMA_STEP
+#undef WOWSR_MMA_HEAD
+}
+
+// First two run-axis taps of a stage.  `first_chunk`: the very first K-step of the tile must overwrite (not
+// accumulate into) the accumulator block of output row yy, which only the row-tap-0 (j = 2) block touches.
+template <int N, int NKS>
+__device__ __forceinline__ void issue_taps01(bool first_chunk, uint32_t acc_base, int yy, int jlo, int jhi, uint32_t col,
+                                             uint64_t a, uint64_t b, uint64_t bj, uint32_t idesc, uint32_t idesc_base) {
+  if (first_chunk) {
+    const uint32_t id1 = idesc_base | ((uint32_t)(N >> 3) << 17);
+    if (jhi == 2) {
+      ptx::mma_f16_ss(acc_base + yy * N, a, b + (uint64_t)(2 * N * 8), id1, 0);
+      if (jlo <= 1) ptx::mma_f16_ss(col, a, bj, idesc_base | ((uint32_t)(((2 - jlo) * N) >> 3) << 17), 1);
+    } else {
+      ptx::mma_f16_ss(col, a, bj, idesc, 1);
+    }
+    mma_group<N, 0, 1, NKS - 1>(col, a, bj, idesc);
+  } else {
+    mma_group<N, 0, 0, NKS>(col, a, bj, idesc);
+  }
+  mma_group<N, 1, 0, NKS>(col, a, bj, idesc);
+}
+
+template <int N>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__ CUtensorMap tmap_v, const ConvParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -220,7 +271,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
   const uint32_t w_smem = a_smem + P.n_stage * TC_ASTAGE;
   const uint32_t ctl_addr = w_smem + P.n_wbuf * P.w_chunk_bytes;
   TcSmemCtl* ctl = reinterpret_cast<TcSmemCtl*>(smem + (ctl_addr - ptx::smem_u32(smem)));
-  const int R = P.R, N = P.N;
+  constexpr int R = N == 64 ? 4 : 8;  // accumulator rows per tile: 2 (double buffer) x R x N = 512 TMEM columns
   const uint32_t tmem_cols = 2u * R * N <= 32 ? 32u : (2u * R * N <= 64 ? 64u : (2u * R * N <= 128 ? 128u : (2u * R * N <= 256 ? 256u : 512u)));
 
   if (threadIdx.x == 128) {
@@ -289,17 +340,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
     // ===================== MMA issuer =====================
     // Per stage (one input row x one 64-channel chunk): 3 run-axis taps x ksteps K-steps, each ONE
     // tcgen05.mma whose N stacks the row-axis taps (N, 2N or 3N columns: tile-edge rows feed fewer output
-    // rows).  The wait for the NEXT stage's TMA data is issued between the MMAs of the current stage so its
-    // latency hides behind queued tensor work.
+    // rows).  The wait for the NEXT stage's TMA data is issued between the taps of the current stage so its
+    // latency hides behind queued tensor work.  The scalar instruction count per stage is what bounds this
+    // warp (a single warp retires ~1 dependent instruction per 5 cycles), hence the templated asm groups.
     const bool leader = ptx::elect_one();
-    const uint32_t desc_hi = (uint32_t)(ptx::smem_desc_sw128(0, 1024, 0) >> 32);
-    const uint32_t a_lo0 = ((a_smem >> 4) & 0x3FFFu) | (1u << 16);
-    const uint32_t b_lo0 = ((w_smem >> 4) & 0x3FFFu) | (1u << 16);
-    const uint32_t idn1 = P.idesc_base | ((uint32_t)(N >> 3) << 17);
-    const uint32_t idn2 = P.idesc_base | ((uint32_t)((2 * N) >> 3) << 17);
-    const uint32_t idn3 = P.idesc_base | ((uint32_t)((3 * N) >> 3) << 17);
+    const uint64_t adesc0 = ptx::smem_desc_sw128(a_smem, 1024, 0);
+    const uint64_t bdesc0 = ptx::smem_desc_sw128(w_smem, 1024, 0);
     const uint32_t full0 = ptx::smem_u32(&ctl->a_full[0]), empty0 = ptx::smem_u32(&ctl->a_empty[0]);
     const int n_my = tile0 < tile_end ? (tile_end - tile0 + tile_step - 1) / tile_step : 0;
+    const uint32_t idesc_base = P.idesc_base;
     int stage = 0;
     uint32_t aphase = 0, wcount = 0;
     bool ok = true;
@@ -315,8 +364,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
       ptx::tc_fence_after();
       const uint32_t acc_base = tmem_base + accbuf * R * N;
       for (int c = 0; c < P.n_chunks && ok; c++) {
-        int ksteps = (P.cin - c * 64) / 16;
-        if (ksteps > 4) ksteps = 4;
+        const bool half_chunk = (P.cin - c * 64) < 64;  // 32 valid channels: 2 K-steps instead of 4
         uint32_t wb;
         if (!(P.w_resident && it > 0)) {
           wb = wcount % P.n_wbuf;
@@ -327,38 +375,22 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
           wb = c;
         }
         ptx::tc_fence_after();
-        const uint32_t b_lo = b_lo0 + ((wb * P.w_chunk_bytes) >> 4);
+        const uint64_t bd = bdesc0 + (uint64_t)((wb * P.w_chunk_bytes) >> 4);
+#pragma unroll 1
         for (int yy = 0; yy < R + 2; yy++) {
           const bool last = (yy == R + 1) && (c == P.n_chunks - 1) && (it == n_my - 1);
           const int jlo = yy < 2 ? 2 - yy : 0;
           const int jhi = R + 1 - yy < 2 ? R + 1 - yy : 2;
-          const int nb = jhi - jlo + 1;
-          const uint32_t idesc = nb == 3 ? idn3 : (nb == 2 ? idn2 : idn1);
+          const uint32_t idesc = idesc_base | ((uint32_t)(((jhi - jlo + 1) * N) >> 3) << 17);
           const uint32_t col = acc_base + (yy - 2 + jlo) * N;
-          const uint32_t a_lo = a_lo0 + stage * (TC_ASTAGE >> 4);
-          const uint32_t bj = b_lo + jlo * N * 8;
+          const uint64_t ad = adesc0 + (uint64_t)(stage * (TC_ASTAGE >> 4));
+          const uint64_t bj = bd + (uint64_t)(jlo * N * 8);
           int ns = stage + 1;
           uint32_t np = aphase;
           if (ns == P.n_stage) { ns = 0; np ^= 1; }
           if (leader) {
-            int k0 = 0;
-            if (c == 0) {  // very first k-step of the tile: the row-tap-0 block initialises output row yy
-              if (jhi == 2) {
-                ptx::mma_f16_ss2(acc_base + yy * N, a_lo, b_lo + 2 * N * 8, desc_hi, idn1, 0);
-                if (jlo <= 1) ptx::mma_f16_ss2(col, a_lo, bj, desc_hi, jlo == 0 ? idn2 : idn1, 1);
-              } else {
-                ptx::mma_f16_ss2(col, a_lo, bj, desc_hi, idesc, 1);
-              }
-              k0 = 1;
-            }
-#pragma unroll
-            for (int kx = 0; kx < 2; kx++) {
-#pragma unroll
-              for (int ks = 0; ks < 4; ks++) {
-                if (kx * 4 + ks >= k0 && ks < ksteps)
-                  ptx::mma_f16_ss2(col, a_lo + (kx * 8 + ks * 2), bj + (kx * 3 * N * 8 + ks * 2), desc_hi, idesc, 1);
-              }
-            }
+            if (half_chunk) issue_taps01<N, 2>(c == 0, acc_base, yy, jlo, jhi, col, ad, bd, bj, idesc, idesc_base);
+            else issue_taps01<N, 4>(c == 0, acc_base, yy, jlo, jhi, col, ad, bd, bj, idesc, idesc_base);
           }
           if (!last) {  // prefetch-wait: the next stage's operands (overlaps the MMAs queued above)
             ok = __all_sync(0xFFFFFFFFu, ptx::mbar_wait(full0 + 8 * ns, np));
@@ -366,11 +398,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
             ptx::tc_fence_after();
           }
           if (leader) {
-#pragma unroll
-            for (int ks = 0; ks < 4; ks++) {
-              if (ks < ksteps)
-                ptx::mma_f16_ss2(col, a_lo + (2 * 8 + ks * 2), bj + (2 * 3 * N * 8 + ks * 2), desc_hi, idesc, 1);
-            }
+            if (half_chunk) mma_group<N, 2, 0, 2>(col, ad, bj, idesc);
+            else mma_group<N, 2, 0, 4>(col, ad, bj, idesc);
             ptx::mma_commit(empty0 + 8 * stage);
           }
           __syncwarp();
@@ -401,7 +430,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
         const int y = vert ? u : v, x = vert ? v : u;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + accbuf * R * N + r * N;
         const bool valid = u < u_lim;
-        if (N >= 32) {
+        if constexpr (N >= 32) {
           for (int c32 = 0; c32 < N / 32; c32++) {
             uint32_t rr[32];
             ptx::tmem_ld32(taddr + c32 * 32, rr);

@@ -13,17 +13,23 @@ struct Cfg {
   int acc_mode;  // 0: one accumulator block; 1: sliding window over 8 blocks like the stacked conv
   int kmode;     // 0: 4 K-steps walk +32 B inside the swizzled row (conv); 1: every MMA uses a fresh 1 KB-aligned A tile
   int iters;     // MMAs per measurement
+  int commit;    // 1: tcgen05.commit to a (free-running) mbarrier after every 12 MMAs, like the conv stages
+  int copy;      // 1: a second warp streams 16.6 KB bulk copies global->smem (stand-in for the TMA row loads)
 };
 
-__global__ void __launch_bounds__(128, 1) mma_bench_kernel(Cfg c, unsigned long long* out) {
+__global__ void __launch_bounds__(128, 1) mma_bench_kernel(Cfg c, unsigned long long* out, const uint8_t* src) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, bar2, bar3;
+  __shared__ volatile int done;
   __shared__ uint32_t tmem_slot;
   const uint32_t base = (ptx::smem_u32(smem) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;  // 1.0 (fp16)
   if (threadIdx.x == 0) {
     ptx::mbar_init(ptx::smem_u32(&bar), 1);
+    ptx::mbar_init(ptx::smem_u32(&bar2), 1);
+    ptx::mbar_init(ptx::smem_u32(&bar3), 1);
+    done = 0;
     ptx::fence_barrier_init();
   }
   if (warp == 0) {
@@ -58,6 +64,7 @@ __global__ void __launch_bounds__(128, 1) mma_bench_kernel(Cfg c, unsigned long 
               const uint64_t b = bd + (uint64_t)(((kx * 8192) >> 4) + ks * 2);
               ptx::mma_f16_ss(tmem + col, a, b, idesc, 1);
             }
+          if (c.commit) ptx::mma_commit(ptx::smem_u32(&bar2));
           stage = (stage + 1) % 6;
           blk++;
         }
@@ -68,6 +75,19 @@ __global__ void __launch_bounds__(128, 1) mma_bench_kernel(Cfg c, unsigned long 
       t1 = clock64();
     }
     if (leader) out[blockIdx.x] = (unsigned long long)(t1 - t0);
+    done = 1;
+  } else if (warp == 1 && c.copy) {
+    // streams row-sized bulk copies into a scratch region (last 20 KB of the A area is not read by the MMAs)
+    if (threadIdx.x == 32) {
+      uint32_t ph = 0;
+      const uint32_t dst = base + 180 * 1024;
+      while (!done) {
+        ptx::mbar_arrive_expect_tx(ptx::smem_u32(&bar3), 16640);
+        ptx::bulk_load(dst, src + (size_t)blockIdx.x * 16640, 16640, ptx::smem_u32(&bar3));
+        ptx::mbar_wait(ptx::smem_u32(&bar3), ph);
+        ph ^= 1;
+      }
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -80,19 +100,20 @@ int main() {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   unsigned long long* d;
   cudaMalloc(&d, sms * 8);
+  uint8_t* src;
+  cudaMalloc(&src, (size_t)sms * 16640);
+  cudaMemset(src, 0, (size_t)sms * 16640);
   const int smem = 200 * 1024 + 2048;
   cudaFuncSetAttribute(mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int iters = 12 * 2000;
   printf("%-6s %-6s %-8s %-6s %-12s %-10s %-8s\n", "N", "shift", "acc", "kmode", "cyc/MMA", "ideal", "eff");
-  for (int grid : {1, sms})
-    for (int n : {32, 48, 64, 96, 128, 192, 256})
-      for (int shift : {0, 1})
-        for (int acc : {0, 1})
-          for (int kmode : {0, 1}) {
-            if (kmode == 1 && shift == 1) continue;
-            if (acc == 1 && n > 96 + 0 && n != 192) continue;
-            Cfg c{n, shift, acc, kmode, iters};
-            mma_bench_kernel<<<grid, 128, smem>>>(c, d);
+  for (int grid : {sms})
+    for (int n : {32, 64, 96, 192})
+      for (int commit : {0, 1})
+        for (int copy : {0, 1}) {
+            const int shift = 1, acc = 1, kmode = 0;
+            Cfg c{n, shift, acc, kmode, iters, commit, copy};
+            mma_bench_kernel<<<grid, 128, smem>>>(c, d, src);
             cudaError_t e = cudaDeviceSynchronize();
             if (e != cudaSuccess) {
               printf("N=%d failed: %s\n", n, cudaGetErrorString(e));
@@ -104,7 +125,7 @@ int main() {
             for (auto v : h) avg += (double)v;
             avg /= grid;
             double per = avg / iters, ideal = n / 2.0;
-            printf("%-6d %-6d %-8d %-6d %-12.1f %-10.1f %-8.2f grid=%d\n", n, shift, acc, kmode, per, ideal, ideal / per, grid);
+            printf("N=%-4d commit=%d copy=%d  cyc/MMA=%-8.1f ideal=%-6.1f eff=%.2f grid=%d\n", n, commit, copy, per, ideal, ideal / per, grid);
           }
   return 0;
 }
