@@ -24,10 +24,11 @@
 
 #include "ptx.cuh"
 
-constexpr int TC_THREADS = 192;       // warps 0-3 epilogue (one per SM sub-partition), warp 4 TMA producer, warp 5 MMA issuer
+constexpr int TC_EPI_WARPS = 8;       // epilogue warps: warp w drains TMEM lane quarter w%4, tile rows r with r%2 == w/4
+constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;  // + TMA producer warp + MMA issuer warp
 // The issuing warps get the HIGHEST warp ids: the sub-partition arbiter favours higher ids, and an MMA issuer
 // that shares a sub-partition with a busy epilogue warp of higher id gets starved (measured).
-constexpr int TC_WARP_TMA = 4, TC_WARP_MMA = 5;
+constexpr int TC_WARP_TMA = TC_EPI_WARPS, TC_WARP_MMA = TC_EPI_WARPS + 1;
 constexpr int TC_RUN = 128;           // output pixels per M-run
 constexpr int TC_AROWS = TC_RUN + 2;  // input pixels per row stage
 constexpr int TC_ABYTES = TC_AROWS * 128;
@@ -274,7 +275,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
   constexpr int R = N == 64 ? 4 : 8;  // accumulator rows per tile: 2 (double buffer) x R x N = 512 TMEM columns
   const uint32_t tmem_cols = 2u * R * N <= 32 ? 32u : (2u * R * N <= 64 ? 64u : (2u * R * N <= 128 ? 128u : (2u * R * N <= 256 ? 256u : 512u)));
 
-  if (threadIdx.x == 128) {
+  if (threadIdx.x == TC_WARP_TMA * 32) {
     ptx::prefetch_tmap(&tmap);  // this CTA's orientation
     for (int i = 0; i < P.n_stage; i++) {
       ptx::mbar_init(ptx::smem_u32(&ctl->a_full[i]), 1);
@@ -286,7 +287,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
     }
     for (int i = 0; i < 2; i++) {
       ptx::mbar_init(ptx::smem_u32(&ctl->t_full[i]), 1);
-      ptx::mbar_init(ptx::smem_u32(&ctl->t_empty[i]), 4);
+      ptx::mbar_init(ptx::smem_u32(&ctl->t_empty[i]), TC_EPI_WARPS);
     }
     ptx::fence_barrier_init();
   }
@@ -413,7 +414,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
     }
   } else {
     // ===================== epilogue warps (TMEM -> registers -> global) =====================
-    const int q = warp;  // warps 0-3: TMEM lane quarter == warp id
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int r_first = warp >> 2;      // two warps per quarter split the tile rows even / odd
     bool ok = true;
     const int u_lim = vert ? P.h : P.w, v_lim = vert ? P.w : P.h;
     for (int tile = tile0, it = 0; tile < tile_end && ok; tile += tile_step, it++) {
@@ -424,7 +426,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
       ok = ptx::mbar_wait(ptx::smem_u32(&ctl->t_full[accbuf]), acc_phase);
       if (!ok) { tc_fail(P, 31); break; }
       ptx::tc_fence_after();
-      for (int r = 0; r < R; r++) {
+      for (int r = r_first; r < R; r += TC_EPI_WARPS / 4) {
         const int v = tc.v0 + r;
         if (v >= v_lim) break;
         const int y = vert ? u : v, x = vert ? v : u;

@@ -19,7 +19,7 @@ struct Cfg {
 
 __global__ void __launch_bounds__(128, 1) mma_bench_kernel(Cfg c, unsigned long long* out, const uint8_t* src) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar, bar2, bar3;
+  __shared__ uint64_t bar, bar2, bar3, cbar[8];
   __shared__ volatile int done;
   __shared__ uint32_t tmem_slot;
   const uint32_t base = (ptx::smem_u32(smem) + 1023u) & ~1023u;
@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(128, 1) mma_bench_kernel(Cfg c, unsigned long 
     ptx::mbar_init(ptx::smem_u32(&bar), 1);
     ptx::mbar_init(ptx::smem_u32(&bar2), 1);
     ptx::mbar_init(ptx::smem_u32(&bar3), 1);
+    for (int k = 0; k < 8; k++) ptx::mbar_init(ptx::smem_u32(&cbar[k]), 1);
     done = 0;
     ptx::fence_barrier_init();
   }
@@ -77,16 +78,26 @@ __global__ void __launch_bounds__(128, 1) mma_bench_kernel(Cfg c, unsigned long 
     if (leader) out[blockIdx.x] = (unsigned long long)(t1 - t0);
     done = 1;
   } else if (warp == 1 && c.copy) {
-    // streams row-sized bulk copies into a scratch region (last 20 KB of the A area is not read by the MMAs)
+    // keeps `c.copy` row-sized bulk copies in flight into a scratch ring (stand-in for the TMA row loads)
     if (threadIdx.x == 32) {
-      uint32_t ph = 0;
-      const uint32_t dst = base + 180 * 1024;
-      while (!done) {
-        ptx::mbar_arrive_expect_tx(ptx::smem_u32(&bar3), 16640);
-        ptx::bulk_load(dst, src + (size_t)blockIdx.x * 16640, 16640, ptx::smem_u32(&bar3));
-        ptx::mbar_wait(ptx::smem_u32(&bar3), ph);
-        ph ^= 1;
+      const int K = c.copy;
+      uint32_t ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      unsigned long long n = 0;
+      for (int k = 0; k < K; k++) {
+        ptx::mbar_arrive_expect_tx(ptx::smem_u32(&cbar[k]), 16640);
+        ptx::bulk_load(base + 128 * 1024 + 50 * 1024 + (k % 1) * 17408, src + ((size_t)blockIdx.x * 8 + k) * 16640, 16640, ptx::smem_u32(&cbar[k]));
       }
+      while (!done) {
+        for (int k = 0; k < K; k++) {
+          ptx::mbar_wait(ptx::smem_u32(&cbar[k]), ph[k]);
+          ph[k] ^= 1;
+          n++;
+          ptx::mbar_arrive_expect_tx(ptx::smem_u32(&cbar[k]), 16640);
+          ptx::bulk_load(base + 128 * 1024 + 50 * 1024, src + ((size_t)blockIdx.x * 8 + k) * 16640, 16640, ptx::smem_u32(&cbar[k]));
+        }
+      }
+      for (int k = 0; k < K; k++) ptx::mbar_wait(ptx::smem_u32(&cbar[k]), ph[k]);
+      out[gridDim.x + blockIdx.x] = n;
     }
   }
   ptx::tc_fence_before();
@@ -99,18 +110,18 @@ int main() {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   unsigned long long* d;
-  cudaMalloc(&d, sms * 8);
+  cudaMalloc(&d, sms * 16);
   uint8_t* src;
-  cudaMalloc(&src, (size_t)sms * 16640);
-  cudaMemset(src, 0, (size_t)sms * 16640);
+  cudaMalloc(&src, (size_t)sms * 8 * 16640);
+  cudaMemset(src, 0, (size_t)sms * 8 * 16640);
   const int smem = 200 * 1024 + 2048;
   cudaFuncSetAttribute(mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int iters = 12 * 2000;
   printf("%-6s %-6s %-8s %-6s %-12s %-10s %-8s\n", "N", "shift", "acc", "kmode", "cyc/MMA", "ideal", "eff");
   for (int grid : {sms})
     for (int n : {32, 64, 96, 192})
-      for (int commit : {0, 1})
-        for (int copy : {0, 1}) {
+      for (int commit : {1})
+        for (int copy : {0, 1, 2, 4, 8}) {
             const int shift = 1, acc = 1, kmode = 0;
             Cfg c{n, shift, acc, kmode, iters, commit, copy};
             mma_bench_kernel<<<grid, 128, smem>>>(c, d, src);
@@ -119,13 +130,15 @@ int main() {
               printf("N=%d failed: %s\n", n, cudaGetErrorString(e));
               return 1;
             }
-            std::vector<unsigned long long> h(grid);
-            cudaMemcpy(h.data(), d, grid * 8, cudaMemcpyDeviceToHost);
+            std::vector<unsigned long long> h(2 * grid);
+            cudaMemcpy(h.data(), d, 2 * grid * 8, cudaMemcpyDeviceToHost);
             double avg = 0;
-            for (auto v : h) avg += (double)v;
+            double ncopy = 0;
+            for (int i = 0; i < grid; i++) { avg += (double)h[i]; ncopy += copy ? (double)h[grid + i] : 0.0; }
             avg /= grid;
+            ncopy /= grid;
             double per = avg / iters, ideal = n / 2.0;
-            printf("N=%-4d commit=%d copy=%d  cyc/MMA=%-8.1f ideal=%-6.1f eff=%.2f grid=%d\n", n, commit, copy, per, ideal, ideal / per, grid);
+            printf("N=%-4d commit=%d copies_in_flight=%d  cyc/MMA=%-8.1f ideal=%-6.1f eff=%.2f  copy B/cyc/SM=%.1f\n", n, commit, copy, per, ideal, ideal / per, ncopy * 16640.0 / (3.0 * avg));
           }
   return 0;
 }
