@@ -161,7 +161,7 @@ int make_tmap(wowsr_ctx* ctx, CUtensorMap* m, const void* base, int C, int W, in
     strides[0] = (cuuint64_t)C * 2 * W;
     strides[1] = (cuuint64_t)C * 2;
   }
-  cuuint32_t box[4] = {64, (cuuint32_t)TC_AROWS, 1, 1};
+  cuuint32_t box[4] = {64, (cuuint32_t)TC_AROWS, 2, 1};  // one pipeline stage = two consecutive rows of the row axis
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base),
                    dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -207,7 +207,7 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
   P.idesc_base = make_idesc_f16(128, 0, L.fp16);
   P.w_chunk_bytes = (uint32_t)L.chunk_bytes;
   size_t wtotal = L.chunk_bytes * L.n_chunks;
-  if (wtotal + 4 * (size_t)TC_ASTAGE + SMEM_SLACK <= SMEM_LIMIT && L.n_chunks <= TC_MAX_WBUF &&
+  if (wtotal + 2 * (size_t)TC_ASTAGE + SMEM_SLACK <= SMEM_LIMIT && L.n_chunks <= TC_MAX_WBUF &&
       !wowsr_opt(ctx, "tc_force_stream", 0)) {
     P.w_resident = 1;
     P.n_wbuf = L.n_chunks;

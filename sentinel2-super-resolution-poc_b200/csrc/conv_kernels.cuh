@@ -32,7 +32,7 @@ constexpr int TC_WARP_TMA = TC_EPI_WARPS, TC_WARP_MMA = TC_EPI_WARPS + 1;
 constexpr int TC_RUN = 128;           // output pixels per M-run
 constexpr int TC_AROWS = TC_RUN + 2;  // input pixels per row stage
 constexpr int TC_ABYTES = TC_AROWS * 128;
-constexpr int TC_ASTAGE = 17408;      // TC_ABYTES rounded up to 1024
+constexpr int TC_ASTAGE = 33792;      // one pipeline stage = two input rows (2 * TC_ABYTES rounded up to 1024)
 constexpr int TC_MAX_STAGES = 10;
 constexpr int TC_MAX_WBUF = 4;
 
@@ -40,6 +40,8 @@ constexpr int CF_STACK = 1;    // stack the three ky taps along N
 constexpr int CF_BASEOFF = 2;  // put (start_addr>>7)&7 into the descriptor base-offset field
 constexpr int CF_FP16 = 4;     // fp16 operands (input activations + weights) instead of bf16
 constexpr int CF_OUT_FP16 = 8; // the layer writes fp16 activations (the next layer's operand type)
+// timing-only debug switches (results are garbage): isolate which role bounds a layer
+constexpr int CF_DBG_NO_TMA = 16, CF_DBG_NO_EPI = 32, CF_DBG_NO_MMA = 64;
 
 struct WinDev {  // output-resolution window record for the final layer
   int X0, Y0;              // origin of this window's output in the stitched image
@@ -305,33 +307,42 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
   // descriptors and barrier addresses live in uniform registers) and predicate only the issuing
   // instructions on one elected lane.  A lane-0-only loop makes nvcc wrap every tcgen05.mma in an
   // elect/R2UR broadcast loop, which costs more than the MMA itself.
+  // A pipeline stage holds TWO consecutive input rows (one TMA box of 2 x 130 pixels x 64 channels): the
+  // tensor pipe accepts only ~2 queued MMAs, so every scalar instruction between MMAs is a bubble and the
+  // per-stage handshake (mbarrier wait, commit, loop) must be amortised over as many MMAs as possible.
+  uint32_t wd = 1u << 26;  // watchdog poll budget; collapses after the first timeout so a bug cannot hang the GPU
   if (warp == TC_WARP_TMA) {
     // ===================== TMA producer =====================
     const bool leader = ptx::elect_one();
     int stage = 0;
     uint32_t aphase = 0, wcount = 0;
-    bool ok = true;
-    for (int tile = tile0, it = 0; tile < tile_end && ok; tile += tile_step, it++) {
+    for (int tile = tile0, it = 0; tile < tile_end; tile += tile_step, it++) {
       const TileCoord tc = decode_tile(P, vert, tile);
-      for (int c = 0; c < P.n_chunks && ok; c++) {
+      for (int c = 0; c < P.n_chunks; c++) {
         if (!(P.w_resident && it > 0)) {
           const uint32_t b = wcount % P.n_wbuf, use = wcount / P.n_wbuf;
-          if (!P.w_resident) ok = __all_sync(0xFFFFFFFFu, ptx::mbar_wait(ptx::smem_u32(&ctl->w_empty[b]), (use & 1) ^ 1));
-          if (!ok) { tc_fail(P, 11); break; }
+          if (!P.w_resident && !ptx::mbar_wait_wd(ptx::smem_u32(&ctl->w_empty[b]), (use & 1) ^ 1, wd)) tc_fail(P, 11);
           if (leader) {
-            ptx::mbar_arrive_expect_tx(ptx::smem_u32(&ctl->w_full[b]), P.w_chunk_bytes);
-            ptx::bulk_load(w_smem + b * P.w_chunk_bytes, wpack + (size_t)c * P.w_chunk_bytes, P.w_chunk_bytes,
-                           ptx::smem_u32(&ctl->w_full[b]));
+            if (P.flags & CF_DBG_NO_TMA) {
+              ptx::mbar_arrive(ptx::smem_u32(&ctl->w_full[b]));
+            } else {
+              ptx::mbar_arrive_expect_tx(ptx::smem_u32(&ctl->w_full[b]), P.w_chunk_bytes);
+              ptx::bulk_load(w_smem + b * P.w_chunk_bytes, wpack + (size_t)c * P.w_chunk_bytes, P.w_chunk_bytes,
+                             ptx::smem_u32(&ctl->w_full[b]));
+            }
           }
           wcount++;
         }
-        for (int yy = 0; yy < R + 2; yy++) {
-          ok = __all_sync(0xFFFFFFFFu, ptx::mbar_wait(ptx::smem_u32(&ctl->a_empty[stage]), aphase ^ 1));
-          if (!ok) { tc_fail(P, 12); break; }
+        for (int sp = 0; sp < (R + 2) / 2; sp++) {
+          if (!ptx::mbar_wait_wd(ptx::smem_u32(&ctl->a_empty[stage]), aphase ^ 1, wd)) tc_fail(P, 12);
           if (leader) {
-            ptx::mbar_arrive_expect_tx(ptx::smem_u32(&ctl->a_full[stage]), TC_ABYTES);
-            ptx::tma_load_4d(a_smem + stage * TC_ASTAGE, &tmap, ptx::smem_u32(&ctl->a_full[stage]), c * 64, tc.u0 - 1,
-                             tc.v0 - 1 + yy, tc.n);
+            if (P.flags & CF_DBG_NO_TMA) {
+              ptx::mbar_arrive(ptx::smem_u32(&ctl->a_full[stage]));
+            } else {
+              ptx::mbar_arrive_expect_tx(ptx::smem_u32(&ctl->a_full[stage]), 2 * TC_ABYTES);
+              ptx::tma_load_4d(a_smem + stage * TC_ASTAGE, &tmap, ptx::smem_u32(&ctl->a_full[stage]), c * 64, tc.u0 - 1,
+                               tc.v0 - 1 + 2 * sp, tc.n);
+            }
           }
           if (++stage == P.n_stage) { stage = 0; aphase ^= 1; }
         }
@@ -339,12 +350,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
     }
   } else if (warp == TC_WARP_MMA) {
     // ===================== MMA issuer =====================
-    // Per stage (one input row x one 64-channel chunk): 3 run-axis taps x ksteps K-steps, each ONE
-    // tcgen05.mma whose N stacks the row-axis taps (N, 2N or 3N columns: tile-edge rows feed fewer output
-    // rows).  The wait for the NEXT stage's TMA data is issued between the taps of the current stage so its
-    // latency hides behind queued tensor work.  The scalar instruction count per stage is what bounds this
-    // warp (a single warp retires ~1 dependent instruction per 5 cycles), hence the templated asm groups.
-    const bool leader = ptx::elect_one();
+    // Per input row and 64-channel chunk: 3 run-axis taps x ksteps K-steps, each ONE tcgen05.mma whose N
+    // stacks the row-axis taps (N, 2N or 3N columns: tile-edge rows feed fewer output rows).  The row loop
+    // is fully unrolled so those shapes are compile-time; the wait for the NEXT stage is issued before the
+    // last tap group of the current one so its latency hides behind queued tensor work.
+    const bool leader = ptx::elect_one() && !(P.flags & CF_DBG_NO_MMA);
+    const bool committer = ptx::elect_one();
     const uint64_t adesc0 = ptx::smem_desc_sw128(a_smem, 1024, 0);
     const uint64_t bdesc0 = ptx::smem_desc_sw128(w_smem, 1024, 0);
     const uint32_t full0 = ptx::smem_u32(&ctl->a_full[0]), empty0 = ptx::smem_u32(&ctl->a_empty[0]);
@@ -352,83 +363,80 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
     const uint32_t idesc_base = P.idesc_base;
     int stage = 0;
     uint32_t aphase = 0, wcount = 0;
-    bool ok = true;
-    if (n_my > 0) {
-      ok = __all_sync(0xFFFFFFFFu, ptx::mbar_wait(full0, 0));
-      if (!ok) tc_fail(P, 23);
-    }
-    for (int it = 0; it < n_my && ok; it++) {
+    if (n_my > 0 && !ptx::mbar_wait_wd(full0, 0, wd)) tc_fail(P, 23);
+    for (int it = 0; it < n_my; it++) {
       const int accbuf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      ok = __all_sync(0xFFFFFFFFu, ptx::mbar_wait(ptx::smem_u32(&ctl->t_empty[accbuf]), acc_phase ^ 1));
-      if (!ok) { tc_fail(P, 21); break; }
+      if (!ptx::mbar_wait_wd(ptx::smem_u32(&ctl->t_empty[accbuf]), acc_phase ^ 1, wd)) tc_fail(P, 21);
       ptx::tc_fence_after();
       const uint32_t acc_base = tmem_base + accbuf * R * N;
-      for (int c = 0; c < P.n_chunks && ok; c++) {
+      for (int c = 0; c < P.n_chunks; c++) {
         const bool half_chunk = (P.cin - c * 64) < 64;  // 32 valid channels: 2 K-steps instead of 4
         uint32_t wb;
         if (!(P.w_resident && it > 0)) {
           wb = wcount % P.n_wbuf;
-          ok = __all_sync(0xFFFFFFFFu, ptx::mbar_wait(ptx::smem_u32(&ctl->w_full[wb]), (wcount / P.n_wbuf) & 1));
-          if (!ok) { tc_fail(P, 22); break; }
+          if (!ptx::mbar_wait_wd(ptx::smem_u32(&ctl->w_full[wb]), (wcount / P.n_wbuf) & 1, wd)) tc_fail(P, 22);
           wcount++;
         } else {
           wb = c;
         }
         ptx::tc_fence_after();
         const uint64_t bd = bdesc0 + (uint64_t)((wb * P.w_chunk_bytes) >> 4);
-#pragma unroll 1
-        for (int yy = 0; yy < R + 2; yy++) {
-          const bool last = (yy == R + 1) && (c == P.n_chunks - 1) && (it == n_my - 1);
-          const int jlo = yy < 2 ? 2 - yy : 0;
-          const int jhi = R + 1 - yy < 2 ? R + 1 - yy : 2;
-          const uint32_t idesc = idesc_base | ((uint32_t)(((jhi - jlo + 1) * N) >> 3) << 17);
-          const uint32_t col = acc_base + (yy - 2 + jlo) * N;
-          const uint64_t ad = adesc0 + (uint64_t)(stage * (TC_ASTAGE >> 4));
-          const uint64_t bj = bd + (uint64_t)(jlo * N * 8);
+        const bool first_chunk = c == 0;
+#pragma unroll
+        for (int sp = 0; sp < (R + 2) / 2; sp++) {
+          const bool last = (sp == (R + 2) / 2 - 1) && (c == P.n_chunks - 1) && (it == n_my - 1);
+          const uint64_t ad0 = adesc0 + (uint64_t)(stage * (TC_ASTAGE >> 4));
           int ns = stage + 1;
           uint32_t np = aphase;
           if (ns == P.n_stage) { ns = 0; np ^= 1; }
-          if (leader) {
-            if (half_chunk) issue_taps01<N, 2>(c == 0, acc_base, yy, jlo, jhi, col, ad, bd, bj, idesc, idesc_base);
-            else issue_taps01<N, 4>(c == 0, acc_base, yy, jlo, jhi, col, ad, bd, bj, idesc, idesc_base);
+#pragma unroll
+          for (int half = 0; half < 2; half++) {
+            const int yy = 2 * sp + half;                      // compile-time after unrolling
+            const int jlo = yy < 2 ? 2 - yy : 0;
+            const int jhi = R + 1 - yy < 2 ? R + 1 - yy : 2;
+            const uint32_t idesc = idesc_base | ((uint32_t)(((jhi - jlo + 1) * N) >> 3) << 17);
+            const uint32_t col = acc_base + (yy - 2 + jlo) * N;
+            const uint64_t ad = ad0 + (uint64_t)(half * (TC_ABYTES >> 4));
+            const uint64_t bj = bd + (uint64_t)(jlo * N * 8);
+            if (leader) {
+              if (half_chunk) issue_taps01<N, 2>(first_chunk, acc_base, yy, jlo, jhi, col, ad, bd, bj, idesc, idesc_base);
+              else issue_taps01<N, 4>(first_chunk, acc_base, yy, jlo, jhi, col, ad, bd, bj, idesc, idesc_base);
+            }
+            if (half == 1 && !last) {  // prefetch-wait for the next stage, hidden behind the MMAs queued above
+              if (!ptx::mbar_wait_wd(full0 + 8 * ns, np, wd)) tc_fail(P, 23);
+              ptx::tc_fence_after();
+            }
+            if (leader) {
+              if (half_chunk) mma_group<N, 2, 0, 2>(col, ad, bj, idesc);
+              else mma_group<N, 2, 0, 4>(col, ad, bj, idesc);
+            }
           }
-          if (!last) {  // prefetch-wait: the next stage's operands (overlaps the MMAs queued above)
-            ok = __all_sync(0xFFFFFFFFu, ptx::mbar_wait(full0 + 8 * ns, np));
-            if (!ok) { tc_fail(P, 23); break; }
-            ptx::tc_fence_after();
-          }
-          if (leader) {
-            if (half_chunk) mma_group<N, 2, 0, 2>(col, ad, bj, idesc);
-            else mma_group<N, 2, 0, 4>(col, ad, bj, idesc);
-            ptx::mma_commit(empty0 + 8 * stage);
-          }
+          if (committer) ptx::mma_commit(empty0 + 8 * stage);
           __syncwarp();
           stage = ns;
           aphase = np;
         }
-        if (!P.w_resident && leader) ptx::mma_commit(ptx::smem_u32(&ctl->w_empty[wb]));
+        if (!P.w_resident && committer) ptx::mma_commit(ptx::smem_u32(&ctl->w_empty[wb]));
       }
-      if (leader) ptx::mma_commit(ptx::smem_u32(&ctl->t_full[accbuf]));
+      if (committer) ptx::mma_commit(ptx::smem_u32(&ctl->t_full[accbuf]));
       __syncwarp();
     }
   } else {
     // ===================== epilogue warps (TMEM -> registers -> global) =====================
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int r_first = warp >> 2;      // two warps per quarter split the tile rows even / odd
-    bool ok = true;
     const int u_lim = vert ? P.h : P.w, v_lim = vert ? P.w : P.h;
-    for (int tile = tile0, it = 0; tile < tile_end && ok; tile += tile_step, it++) {
+    for (int tile = tile0, it = 0; tile < tile_end; tile += tile_step, it++) {
       const TileCoord tc = decode_tile(P, vert, tile);
       const int n = tc.n, u = tc.u0 + q * 32 + lane;
       const int accbuf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      ok = ptx::mbar_wait(ptx::smem_u32(&ctl->t_full[accbuf]), acc_phase);
-      if (!ok) { tc_fail(P, 31); break; }
+      if (!ptx::mbar_wait_wd(ptx::smem_u32(&ctl->t_full[accbuf]), acc_phase, wd)) tc_fail(P, 31);
       ptx::tc_fence_after();
       for (int r = r_first; r < R; r += TC_EPI_WARPS / 4) {
         const int v = tc.v0 + r;
-        if (v >= v_lim) break;
+        if (v >= v_lim || (P.flags & CF_DBG_NO_EPI)) break;
         const int y = vert ? u : v, x = vert ? v : u;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + accbuf * R * N + r * N;
         const bool valid = u < u_lim;

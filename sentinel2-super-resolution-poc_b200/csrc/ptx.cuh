@@ -47,6 +47,16 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, uint32_
   return false;
 }
 
+// Watchdog variant for hot loops: no data-dependent control flow in the caller.  After the first timeout the
+// budget collapses to a few polls, so the kernel drains quickly (with garbage results and an error flag).
+__device__ __forceinline__ bool mbar_wait_wd(uint32_t bar, uint32_t parity, uint32_t& budget) {
+#pragma unroll 1
+  for (uint32_t i = 0; i < budget; i++)
+    if (mbar_try_wait(bar, parity)) return true;
+  budget = 4;
+  return false;
+}
+
 // ---- TMA ------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
