@@ -74,6 +74,7 @@ struct ConvParams {
   float* out_f32_b;
   void* out_t;           // T output, pixel stride out_stride (elements), channel offset out_choff
   int out_stride, out_choff, out_rep;
+  int f32_wpb;           // > 0: fp32 buffers use the warp-blocked layout with this many 32-pixel blocks per row
   // final layer
   int final;
   uint8_t* out_u8;
@@ -109,41 +110,78 @@ __device__ __forceinline__ void epilogue_pixel(const ConvParams& P, int n, int y
     return;
   }
   const long long pix = ((long long)n * P.h + y) * P.w + x;
-  if (P.res1) {
-    const float4* r = reinterpret_cast<const float4*>(P.res1 + pix * 64 + ch0);
+  if (P.f32_wpb) {
+    // fp32 trunk buffers in the warp-blocked layout [row][x/32][channel][x%32]: the 32 lanes of an epilogue
+    // warp own 32 consecutive x, so every per-channel access is one fully coalesced 128-byte wavefront
+    // (the plain [pixel][64 ch] layout costs 32 wavefronts per 16-byte-per-lane access).
+    const long long fb = ((((long long)n * P.h + y) * P.f32_wpb + (x >> 5)) * 64 + ch0) * 32 + (x & 31);
+    if (P.res1) {
+      const float* r = P.res1 + fb;
+      float t[NCH];
 #pragma unroll
-    for (int i = 0; i < NCH / 4; i++) {
-      float4 t = r[i];
-      v[4 * i + 0] = __fadd_rn(__fmul_rn(v[4 * i + 0], P.scale1), t.x);
-      v[4 * i + 1] = __fadd_rn(__fmul_rn(v[4 * i + 1], P.scale1), t.y);
-      v[4 * i + 2] = __fadd_rn(__fmul_rn(v[4 * i + 2], P.scale1), t.z);
-      v[4 * i + 3] = __fadd_rn(__fmul_rn(v[4 * i + 3], P.scale1), t.w);
+      for (int i = 0; i < NCH; i++) t[i] = r[i * 32];
+#pragma unroll
+      for (int i = 0; i < NCH; i++) v[i] = __fadd_rn(__fmul_rn(v[i], P.scale1), t[i]);
     }
-  }
-  if (P.res2) {
-    const float4* r = reinterpret_cast<const float4*>(P.res2 + pix * 64 + ch0);
+    if (P.res2) {
+      const float* r = P.res2 + fb;
+      float t[NCH];
 #pragma unroll
-    for (int i = 0; i < NCH / 4; i++) {
-      float4 t = r[i];
-      v[4 * i + 0] = __fadd_rn(__fmul_rn(v[4 * i + 0], P.scale2), t.x);
-      v[4 * i + 1] = __fadd_rn(__fmul_rn(v[4 * i + 1], P.scale2), t.y);
-      v[4 * i + 2] = __fadd_rn(__fmul_rn(v[4 * i + 2], P.scale2), t.z);
-      v[4 * i + 3] = __fadd_rn(__fmul_rn(v[4 * i + 3], P.scale2), t.w);
+      for (int i = 0; i < NCH; i++) t[i] = r[i * 32];
+#pragma unroll
+      for (int i = 0; i < NCH; i++) v[i] = __fadd_rn(__fmul_rn(v[i], P.scale2), t[i]);
     }
-  }
-  if (P.act) {
+    if (P.act) {
 #pragma unroll
-    for (int i = 0; i < NCH; i++) v[i] = v[i] >= 0.0f ? v[i] : __fmul_rn(v[i], 0.2f);
-  }
-  if (P.out_f32_a) {
-    float4* o = reinterpret_cast<float4*>(P.out_f32_a + pix * 64 + ch0);
+      for (int i = 0; i < NCH; i++) v[i] = v[i] >= 0.0f ? v[i] : __fmul_rn(v[i], 0.2f);
+    }
+    if (P.out_f32_a) {
+      float* o = P.out_f32_a + fb;
 #pragma unroll
-    for (int i = 0; i < NCH / 4; i++) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-  }
-  if (P.out_f32_b) {
-    float4* o = reinterpret_cast<float4*>(P.out_f32_b + pix * 64 + ch0);
+      for (int i = 0; i < NCH; i++) o[i * 32] = v[i];
+    }
+    if (P.out_f32_b) {
+      float* o = P.out_f32_b + fb;
 #pragma unroll
-    for (int i = 0; i < NCH / 4; i++) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      for (int i = 0; i < NCH; i++) o[i * 32] = v[i];
+    }
+  } else {
+    if (P.res1) {
+      const float4* r = reinterpret_cast<const float4*>(P.res1 + pix * 64 + ch0);
+#pragma unroll
+      for (int i = 0; i < NCH / 4; i++) {
+        float4 t = r[i];
+        v[4 * i + 0] = __fadd_rn(__fmul_rn(v[4 * i + 0], P.scale1), t.x);
+        v[4 * i + 1] = __fadd_rn(__fmul_rn(v[4 * i + 1], P.scale1), t.y);
+        v[4 * i + 2] = __fadd_rn(__fmul_rn(v[4 * i + 2], P.scale1), t.z);
+        v[4 * i + 3] = __fadd_rn(__fmul_rn(v[4 * i + 3], P.scale1), t.w);
+      }
+    }
+    if (P.res2) {
+      const float4* r = reinterpret_cast<const float4*>(P.res2 + pix * 64 + ch0);
+#pragma unroll
+      for (int i = 0; i < NCH / 4; i++) {
+        float4 t = r[i];
+        v[4 * i + 0] = __fadd_rn(__fmul_rn(v[4 * i + 0], P.scale2), t.x);
+        v[4 * i + 1] = __fadd_rn(__fmul_rn(v[4 * i + 1], P.scale2), t.y);
+        v[4 * i + 2] = __fadd_rn(__fmul_rn(v[4 * i + 2], P.scale2), t.z);
+        v[4 * i + 3] = __fadd_rn(__fmul_rn(v[4 * i + 3], P.scale2), t.w);
+      }
+    }
+    if (P.act) {
+#pragma unroll
+      for (int i = 0; i < NCH; i++) v[i] = v[i] >= 0.0f ? v[i] : __fmul_rn(v[i], 0.2f);
+    }
+    if (P.out_f32_a) {
+      float4* o = reinterpret_cast<float4*>(P.out_f32_a + pix * 64 + ch0);
+#pragma unroll
+      for (int i = 0; i < NCH / 4; i++) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
+    if (P.out_f32_b) {
+      float4* o = reinterpret_cast<float4*>(P.out_f32_b + pix * 64 + ch0);
+#pragma unroll
+      for (int i = 0; i < NCH / 4; i++) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
   }
   if (P.out_t) {
     uint32_t pk[NCH / 2];
@@ -542,6 +580,7 @@ struct FirstParams {
   int Nw, h, w;
   const float* weight;  // [ky][kx][ci][64] fp32
   const float* bias;    // [64]
+  int f32_wpb;          // > 0: warp-blocked fp32 layout (see ConvParams::f32_wpb)
   float* f32_a;         // fp32 [pix][64] outputs (feat / trunk / rrdb_in), any may be null
   float* f32_b;
   float* f32_c;
@@ -593,9 +632,15 @@ conv_first_kernel(const FirstParams P) {
 #pragma unroll
   for (int k = 0; k < 3; k++)
     if (outs[k]) {
-      float4* o = reinterpret_cast<float4*>(outs[k] + pix * 64 + qd * 16);
+      if (P.f32_wpb) {
+        float* o = outs[k] + ((((long long)n * P.h + y) * P.f32_wpb + (x >> 5)) * 64 + qd * 16) * 32 + (x & 31);
 #pragma unroll
-      for (int i = 0; i < 4; i++) o[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+        for (int i = 0; i < 16; i++) o[i * 32] = acc[i];
+      } else {
+        float4* o = reinterpret_cast<float4*>(outs[k] + pix * 64 + qd * 16);
+#pragma unroll
+        for (int i = 0; i < 4; i++) o[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+      }
     }
   if (P.out_t) {
     uint32_t pk[8];
