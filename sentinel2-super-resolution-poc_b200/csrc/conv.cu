@@ -184,7 +184,7 @@ struct LayerIO {
   void* out_t = nullptr;
   int out_stride = 0, out_choff = 0, out_rep = 1;
   int out_fp16 = 0;
-  int f32_wpb = 0;
+  F32Layout f32 = {0, 0, 0, 0, 0};
   int final = 0;
   uint8_t* out_u8 = nullptr;
   long long out_u8_pitch = 0;
@@ -228,7 +228,7 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
   P.act = io.act; P.scale1 = io.scale1; P.res1 = io.res1; P.scale2 = io.scale2; P.res2 = io.res2;
   P.out_f32_a = io.out_f32_a; P.out_f32_b = io.out_f32_b;
   P.out_t = io.out_t; P.out_stride = io.out_stride; P.out_choff = io.out_choff; P.out_rep = io.out_rep;
-  P.f32_wpb = io.f32_wpb;
+  P.f32 = io.f32;
   P.final = io.final; P.out_u8 = io.out_u8; P.out_u8_pitch = io.out_u8_pitch;
   P.out_img_f32 = io.out_img_f32; P.out_img_f32_pitch = io.out_img_f32_pitch; P.wins = io.wins;
   P.err_flag = (int*)net->err.p;
@@ -314,8 +314,19 @@ int rrdbnet_batch(wowsr_ctx* ctx, ConvNet* net, const uint8_t* img, long long pi
                   uint8_t* out, long long out_pitch, float* out_f32, long long out_f32_pitch, cudaStream_t st) {
   const int h = wins[0].y1 - wins[0].y0, w = wins[0].x1 - wins[0].x0;
   const size_t px = (size_t)nb * h * w;
-  const int wpb = (w + 31) / 32;                       // fp32 trunk buffers: warp-blocked layout
-  const size_t pxb = (size_t)nb * h * wpb * 32;
+  // fp32 trunk buffers: warp-blocked layout (F32Layout); the remainder strip is blocked along y when the
+  // body layers will cover it with vertical tiles
+  F32Layout fl;
+  {
+    const int wm = w / TC_RUN * TC_RUN, rem = w - wm;
+    const bool strip = rem > 0 && wm > 0 && h >= 64;
+    fl.x0 = strip ? wm : w;
+    fl.wpb = strip ? wm / 32 : (w + 31) / 32;
+    fl.rem = strip ? rem : 0;
+    fl.hpb = (h + 31) / 32;
+    fl.strip_off = (long long)nb * h * fl.wpb * 32 * 64;
+  }
+  const size_t pxb = (size_t)nb * h * fl.wpb * 32 + (size_t)nb * fl.rem * fl.hpb * 32;
   const bool body16 = net->body_fp16, tail16 = net->tail_fp16;
   if (int e = wowsr_ensure(ctx, net->dense0, px * 192 * 2)) return e;
   if (int e = wowsr_ensure(ctx, net->dense1, px * 192 * 2)) return e;
@@ -345,7 +356,7 @@ int rrdbnet_batch(wowsr_ctx* ctx, ConvNet* net, const uint8_t* img, long long pi
     F.img = img; F.pitch = pitch; F.cin = 3; F.win_xy = (const int*)net->winxy.p;
     F.Nw = nb; F.h = h; F.w = w; F.weight = net->first_w; F.bias = net->first_b;
     F.f32_a = (float*)net->feat.p; F.f32_b = (float*)net->trunk.p; F.f32_c = (float*)net->rrdb.p;
-    F.f32_wpb = wpb;
+    F.f32 = fl;
     F.out_t = net->dense0.p; F.out_stride = 192; F.out_fp16 = body16; F.in_scale_div = 255.0f;
     dim3 grid((unsigned)((px + 127) / 128), 4);
     conv_first_kernel<<<grid, 128, 0, st>>>(F);
@@ -366,7 +377,7 @@ int rrdbnet_batch(wowsr_ctx* ctx, ConvNet* net, const uint8_t* img, long long pi
       }
       LayerIO io;
       io.in = cur; io.in_C = 192; io.Nw = nb; io.h = h; io.w = w;
-      io.f32_wpb = wpb;
+      io.f32 = fl;
       io.scale1 = 0.2f; io.res1 = (const float*)net->trunk.p;
       io.out_f32_a = (float*)net->trunk.p;
       if (r == 2) {
@@ -383,7 +394,7 @@ int rrdbnet_batch(wowsr_ctx* ctx, ConvNet* net, const uint8_t* img, long long pi
   {  // conv_body + long skip, written nearest-x2 replicated for conv_up1
     LayerIO io;
     io.in = cur; io.in_C = 192; io.Nw = nb; io.h = h; io.w = w;
-    io.f32_wpb = wpb;
+    io.f32 = fl;
     io.scale1 = 1.0f; io.res1 = (const float*)net->feat.p;
     io.out_t = net->up1.p; io.out_stride = 64; io.out_rep = 2; io.out_fp16 = tail16;
     if (int e = run_conv(ctx, net, net->layers[li++], io, st)) return e;

@@ -48,6 +48,24 @@ struct WinDev {  // output-resolution window record for the final layer
   int OX0, OY0, OX1, OY1;  // owned rectangle in the stitched image (last-writer-wins resolved)
 };
 
+// Warp-blocked layout of the fp32 trunk buffers (feat / trunk / rrdb_in).  The 32 lanes of an epilogue warp
+// own 32 consecutive pixels along the tile's run axis and each lane touches all channels of its pixel, so
+// the buffers are stored [..][32-pixel block][channel][pixel in block]: every per-channel access of a warp is
+// ONE coalesced 128-byte wavefront (the plain [pixel][64 ch] layout costs 32 wavefronts per access).
+// Pixels x < x0 are blocked along x (horizontal tiles); the remainder strip x >= x0 is blocked along y
+// (vertical tiles) and stored after the main region.
+struct F32Layout {
+  int wpb;              // 32-pixel blocks per row of the main region (0: plain layout)
+  int x0;               // first strip column (== w when there is no strip)
+  int hpb;              // 32-pixel blocks per strip column
+  int rem;              // strip width
+  long long strip_off;  // element offset of the strip region
+};
+__device__ __forceinline__ long long f32_index(const F32Layout& L, int h, int n, int y, int x, int ch) {
+  if (x < L.x0) return ((((long long)n * h + y) * L.wpb + (x >> 5)) * 64 + ch) * 32 + (x & 31);
+  return L.strip_off + ((((long long)n * L.rem + (x - L.x0)) * L.hpb + (y >> 5)) * 64 + ch) * 32 + (y & 31);
+}
+
 struct ConvParams {
   int Nw, h, w;       // windows in the batch, layer resolution
   int cin, n_chunks;  // input channels (multiple of 16), 64-channel chunks
@@ -74,7 +92,7 @@ struct ConvParams {
   float* out_f32_b;
   void* out_t;           // T output, pixel stride out_stride (elements), channel offset out_choff
   int out_stride, out_choff, out_rep;
-  int f32_wpb;           // > 0: fp32 buffers use the warp-blocked layout with this many 32-pixel blocks per row
+  F32Layout f32;         // layout of the fp32 trunk buffers (wpb == 0: plain [pixel][64])
   // final layer
   int final;
   uint8_t* out_u8;
@@ -110,11 +128,8 @@ __device__ __forceinline__ void epilogue_pixel(const ConvParams& P, int n, int y
     return;
   }
   const long long pix = ((long long)n * P.h + y) * P.w + x;
-  if (P.f32_wpb) {
-    // fp32 trunk buffers in the warp-blocked layout [row][x/32][channel][x%32]: the 32 lanes of an epilogue
-    // warp own 32 consecutive x, so every per-channel access is one fully coalesced 128-byte wavefront
-    // (the plain [pixel][64 ch] layout costs 32 wavefronts per 16-byte-per-lane access).
-    const long long fb = ((((long long)n * P.h + y) * P.f32_wpb + (x >> 5)) * 64 + ch0) * 32 + (x & 31);
+  if (P.f32.wpb) {
+    const long long fb = f32_index(P.f32, P.h, n, y, x, ch0);
     if (P.res1) {
       const float* r = P.res1 + fb;
       float t[NCH];
@@ -580,7 +595,7 @@ struct FirstParams {
   int Nw, h, w;
   const float* weight;  // [ky][kx][ci][64] fp32
   const float* bias;    // [64]
-  int f32_wpb;          // > 0: warp-blocked fp32 layout (see ConvParams::f32_wpb)
+  F32Layout f32;        // layout of the fp32 outputs
   float* f32_a;         // fp32 [pix][64] outputs (feat / trunk / rrdb_in), any may be null
   float* f32_b;
   float* f32_c;
@@ -632,8 +647,8 @@ conv_first_kernel(const FirstParams P) {
 #pragma unroll
   for (int k = 0; k < 3; k++)
     if (outs[k]) {
-      if (P.f32_wpb) {
-        float* o = outs[k] + ((((long long)n * P.h + y) * P.f32_wpb + (x >> 5)) * 64 + qd * 16) * 32 + (x & 31);
+      if (P.f32.wpb) {
+        float* o = outs[k] + f32_index(P.f32, P.h, n, y, x, qd * 16);
 #pragma unroll
         for (int i = 0; i < 16; i++) o[i * 32] = acc[i];
       } else {
