@@ -222,7 +222,9 @@ def run_ours(args):
             return scene.run_scene(backend, dimg, tile, post=wl["post"], gather=True)
         # post-process-only workload: the "SR output" is a nearest-x4 of the input
         sr = dimg.repeat_interleave(4, 0).repeat_interleave(4, 1).contiguous()
-        return None, ws.app.wow_sr.enhance_for_crops_cuda(sr), None
+        out = torch.empty_like(sr)
+        up._h.post_process_dev(sr.data_ptr(), out.data_ptr(), sr.shape[0], sr.shape[1], params, stream=torch.cuda.current_stream().cuda_stream)
+        return None, out, None
 
     def barrier():
         if world > 1:

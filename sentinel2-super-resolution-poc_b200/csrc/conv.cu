@@ -183,6 +183,10 @@ struct LayerIO {
   float* out_f32_b = nullptr;
   void* out_t = nullptr;
   int out_stride = 0, out_choff = 0, out_rep = 1;
+  int out_ps = 0;
+  float final_scale = 255.0f;
+  float final_add[3] = {0.0f, 0.0f, 0.0f};
+  int final_round = 0;
   int out_fp16 = 0;
   F32Layout f32 = {0, 0, 0, 0, 0};
   int final = 0;
@@ -229,6 +233,8 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
   P.out_f32_a = io.out_f32_a; P.out_f32_b = io.out_f32_b;
   P.out_t = io.out_t; P.out_stride = io.out_stride; P.out_choff = io.out_choff; P.out_rep = io.out_rep;
   P.f32 = io.f32;
+  P.out_ps = io.out_ps; P.final_scale = io.final_scale; P.final_round = io.final_round;
+  for (int i = 0; i < 3; i++) P.final_add[i] = io.final_add[i];
   P.final = io.final; P.out_u8 = io.out_u8; P.out_u8_pitch = io.out_u8_pitch;
   P.out_img_f32 = io.out_img_f32; P.out_img_f32_pitch = io.out_img_f32_pitch; P.wins = io.wins;
   P.err_flag = (int*)net->err.p;
@@ -594,9 +600,169 @@ extern "C" int wowsr_conv3x3_host(wowsr_ctx* ctx, const float* in, int32_t n, in
   return e;
 }
 
-extern "C" int wowsr_load_edsr(wowsr_ctx* ctx, int32_t, int32_t, float, const float* const*, int32_t, int32_t) {
-  return wowsr_fail(ctx, WOWSR_ERR_UNSUPPORTED, "EDSR path not built yet");
+// ---------------------------------------------------------------------------------------------
+// EDSR-baseline x4 ("farm SR" variant named by BASELINE; the reference reaches it through
+// cv2.dnn_superres with an external EDSR_x4.pb, super_resolution.py:92-124,196 — third-party, parity
+// unpinned).  Layer list restated in oracle/edsr_ref.py; tensor order documented in include/wowsr.h.
+// ---------------------------------------------------------------------------------------------
+
+namespace {
+const float kEdsrMean[3] = {103.1545782f, 111.561547f, 114.35629928f};  // BGR, 0..255 range
+
+F32Layout plain_blocked(int nb, int h, int w) {
+  F32Layout fl;
+  const int wm = w / TC_RUN * TC_RUN, rem = w - wm;
+  const bool strip = rem > 0 && wm > 0 && h >= 64;
+  fl.x0 = strip ? wm : w;
+  fl.wpb = strip ? wm / 32 : (w + 31) / 32;
+  fl.rem = strip ? rem : 0;
+  fl.hpb = (h + 31) / 32;
+  fl.strip_off = (long long)nb * h * fl.wpb * 32 * 64;
+  return fl;
 }
-extern "C" int wowsr_edsr_upsample_host(wowsr_ctx* ctx, const uint8_t*, int32_t, int32_t, uint8_t*, float*) {
-  return wowsr_fail(ctx, WOWSR_ERR_UNSUPPORTED, "EDSR path not built yet");
+}  // namespace
+
+extern "C" int wowsr_load_edsr(wowsr_ctx* ctx, int32_t num_block, int32_t num_feat, float res_scale,
+                               const float* const* tensors, int32_t n_tensors, int32_t precision) {
+  if (!ctx || !tensors) return WOWSR_ERR_ARG;
+  if (num_feat != 64) return wowsr_fail(ctx, WOWSR_ERR_UNSUPPORTED, "EDSR-baseline has 64 features");
+  const int n_convs = 2 * num_block + 5;
+  if (n_tensors != 2 * n_convs) return wowsr_fail(ctx, WOWSR_ERR_ARG, "expected %d tensors, got %d", 2 * n_convs, n_tensors);
+  DeviceGuard g(ctx->device);
+  wowsr_net_free(ctx->edsr);
+  ctx->edsr = nullptr;
+  ConvNet* net = new ConvNet();
+  net->kind = 1;
+  net->num_block = num_block;
+  net->res_scale = res_scale;
+  net->body_fp16 = net->tail_fp16 = precision != WOWSR_PREC_BF16;  // EDSR works on the 0..255 range: fp16 unless bf16_pure
+  const bool f16 = net->body_fp16;
+  int t = 0;
+  int e = upload_first(ctx, net, tensors[0], tensors[1], 3, 64);
+  t = 2;
+  for (int i = 0; i < 2 * num_block + 1 && !e; i++) {  // resblock convs + body_end
+    net->layers.emplace_back();
+    e = upload_layer(ctx, net->layers.back(), tensors[t], tensors[t + 1], 64, 64, f16);
+    t += 2;
+  }
+  for (int u = 0; u < 2 && !e; u++) {  // 64 -> 256 + depth-to-space(2), split into 4 groups of 64 permuted channels
+    const float* w = tensors[t];
+    const float* b = tensors[t + 1];
+    for (int grp = 0; grp < 4 && !e; grp++) {
+      std::vector<float> wg((size_t)64 * 64 * 9), bg(64);
+      for (int s = 0; s < 4; s++)
+        for (int i = 0; i < 16; i++) {
+          const int dst = s * 16 + i, src = (16 * grp + i) * 4 + s;  // PixelShuffle: channel c*4 + s -> (c, sub-pixel s)
+          memcpy(&wg[(size_t)dst * 64 * 9], &w[(size_t)src * 64 * 9], sizeof(float) * 64 * 9);
+          bg[dst] = b[src];
+        }
+      net->layers.emplace_back();
+      e = upload_layer(ctx, net->layers.back(), wg.data(), bg.data(), 64, 64, f16);
+    }
+    t += 2;
+  }
+  if (!e) {
+    net->layers.emplace_back();
+    e = upload_layer(ctx, net->layers.back(), tensors[t], tensors[t + 1], 64, 3, f16);
+  }
+  if (!e) e = wowsr_ensure(ctx, net->err, 4);
+  if (!e && cudaMemset(net->err.p, 0, 4) != cudaSuccess) e = wowsr_fail(ctx, WOWSR_ERR_CUDA, "memset");
+  if (e) {
+    wowsr_net_free(net);
+    return e;
+  }
+  ctx->edsr = net;
+  return WOWSR_OK;
+}
+
+extern "C" int wowsr_edsr_upsample_host(wowsr_ctx* ctx, const uint8_t* img_host, int32_t H, int32_t W, uint8_t* out_host,
+                                        float* out_f32_host) {
+  if (!ctx || !img_host || !out_host || H < 1 || W < 1) return WOWSR_ERR_ARG;
+  ConvNet* net = ctx->edsr;
+  if (!net) return wowsr_fail(ctx, WOWSR_ERR_STATE, "wowsr_load_edsr has not been called");
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = 0;
+  const size_t px = (size_t)H * W, in_bytes = px * 3, out_bytes = in_bytes * 16;
+  const bool f16 = net->body_fp16;
+  const F32Layout fl = plain_blocked(1, H, W);
+  const size_t pxb = (size_t)H * fl.wpb * 32 + (size_t)fl.rem * fl.hpb * 32;
+  if (int e = wowsr_ensure(ctx, ctx->img_in, in_bytes)) return e;
+  if (int e = wowsr_ensure(ctx, ctx->img_out, out_bytes)) return e;
+  if (out_f32_host)
+    if (int e = wowsr_ensure(ctx, ctx->img_out_f32, out_bytes * 4)) return e;
+  if (int e = wowsr_ensure(ctx, net->dense0, px * 64 * 2)) return e;
+  if (int e = wowsr_ensure(ctx, net->dense1, px * 64 * 2)) return e;
+  if (int e = wowsr_ensure(ctx, net->feat, pxb * 64 * 4)) return e;
+  if (int e = wowsr_ensure(ctx, net->trunk, pxb * 64 * 4)) return e;
+  if (int e = wowsr_ensure(ctx, net->up1, px * 4 * 64 * 2)) return e;
+  if (int e = wowsr_ensure(ctx, net->hra, px * 16 * 64 * 2)) return e;
+  if (int e = wowsr_ensure(ctx, net->wins, sizeof(WinDev))) return e;
+  if (int e = wowsr_ensure(ctx, net->winxy, 8)) return e;
+  WinDev wd{0, 0, 0, 0, 4 * W, 4 * H};
+  int wxy[2] = {0, 0};
+  WCUDA(ctx, cudaMemcpyAsync(ctx->img_in.p, img_host, in_bytes, cudaMemcpyHostToDevice, st));
+  WCUDA(ctx, cudaMemcpyAsync(net->wins.p, &wd, sizeof wd, cudaMemcpyHostToDevice, st));
+  WCUDA(ctx, cudaMemcpyAsync(net->winxy.p, wxy, 8, cudaMemcpyHostToDevice, st));
+  WCUDA(ctx, cudaStreamSynchronize(st));
+  {
+    FirstParams F;
+    memset(&F, 0, sizeof F);
+    F.img = (const uint8_t*)ctx->img_in.p; F.pitch = (long long)W * 3; F.cin = 3; F.win_xy = (const int*)net->winxy.p;
+    F.Nw = 1; F.h = H; F.w = W; F.weight = net->first_w; F.bias = net->first_b;
+    F.f32 = fl;
+    F.f32_a = (float*)net->feat.p; F.f32_b = (float*)net->trunk.p;
+    F.out_t = net->dense0.p; F.out_stride = 64; F.out_fp16 = f16; F.in_scale_div = 1.0f;
+    for (int i = 0; i < 3; i++) F.sub[i] = kEdsrMean[i];
+    dim3 grid((unsigned)((px + 127) / 128), 4);
+    conv_first_kernel<<<grid, 128, 0, st>>>(F);
+    WLAUNCH_CHECK(ctx);
+  }
+  void* a = net->dense0.p;
+  void* b = net->dense1.p;
+  size_t li = 0;
+  for (int blk = 0; blk < net->num_block; blk++) {
+    LayerIO io;
+    io.in = a; io.in_C = 64; io.Nw = 1; io.h = H; io.w = W; io.act = 2;
+    io.out_t = b; io.out_stride = 64; io.out_fp16 = f16;
+    if (int e = run_conv(ctx, net, net->layers[li++], io, st)) return e;
+    LayerIO io2;
+    io2.in = b; io2.in_C = 64; io2.Nw = 1; io2.h = H; io2.w = W;
+    io2.f32 = fl; io2.scale1 = net->res_scale; io2.res1 = (const float*)net->trunk.p; io2.out_f32_a = (float*)net->trunk.p;
+    io2.out_t = a; io2.out_stride = 64; io2.out_fp16 = f16;
+    if (int e = run_conv(ctx, net, net->layers[li++], io2, st)) return e;
+  }
+  {  // body end + global skip
+    LayerIO io;
+    io.in = a; io.in_C = 64; io.Nw = 1; io.h = H; io.w = W;
+    io.f32 = fl; io.scale1 = 1.0f; io.res1 = (const float*)net->feat.p;
+    io.out_t = b; io.out_stride = 64; io.out_fp16 = f16;
+    if (int e = run_conv(ctx, net, net->layers[li++], io, st)) return e;
+  }
+  for (int grp = 0; grp < 4; grp++) {  // up1: 64 -> 256, depth-to-space -> [2H,2W,64]
+    LayerIO io;
+    io.in = b; io.in_C = 64; io.Nw = 1; io.h = H; io.w = W;
+    io.out_t = net->up1.p; io.out_stride = 64; io.out_choff = 16 * grp; io.out_ps = 1; io.out_fp16 = f16;
+    if (int e = run_conv(ctx, net, net->layers[li++], io, st)) return e;
+  }
+  for (int grp = 0; grp < 4; grp++) {  // up2 -> [4H,4W,64]
+    LayerIO io;
+    io.in = net->up1.p; io.in_C = 64; io.Nw = 1; io.h = 2 * H; io.w = 2 * W;
+    io.out_t = net->hra.p; io.out_stride = 64; io.out_choff = 16 * grp; io.out_ps = 1; io.out_fp16 = f16;
+    if (int e = run_conv(ctx, net, net->layers[li++], io, st)) return e;
+  }
+  {  // tail 64 -> 3, + mean, round, saturate
+    LayerIO io;
+    io.in = net->hra.p; io.in_C = 64; io.Nw = 1; io.h = 4 * H; io.w = 4 * W;
+    io.final = 1; io.final_scale = 1.0f; io.final_round = 1;
+    for (int i = 0; i < 3; i++) io.final_add[i] = kEdsrMean[i];
+    io.out_u8 = (uint8_t*)ctx->img_out.p; io.out_u8_pitch = (long long)W * 4 * 3;
+    io.out_img_f32 = out_f32_host ? (float*)ctx->img_out_f32.p : nullptr; io.out_img_f32_pitch = (long long)W * 4 * 3;
+    io.wins = (const WinDev*)net->wins.p;
+    if (int e = run_conv(ctx, net, net->layers[li++], io, st)) return e;
+  }
+  if (int e = check_err_flag(ctx, net, st)) return e;
+  WCUDA(ctx, cudaMemcpyAsync(out_host, ctx->img_out.p, out_bytes, cudaMemcpyDeviceToHost, st));
+  if (out_f32_host) WCUDA(ctx, cudaMemcpyAsync(out_f32_host, ctx->img_out_f32.p, out_bytes * 4, cudaMemcpyDeviceToHost, st));
+  WCUDA(ctx, cudaStreamSynchronize(st));
+  return WOWSR_OK;
 }

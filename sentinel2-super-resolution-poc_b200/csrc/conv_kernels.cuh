@@ -83,7 +83,7 @@ struct ConvParams {
   const void* in;        // simple kernel: input activations (T), pixel stride in_stride, offset 0
   int in_stride;
   // epilogue
-  int act;               // LeakyReLU(0.2)
+  int act;               // 1: LeakyReLU(0.2)   2: ReLU
   float scale1;          // v = v*scale1 + res1
   const float* res1;     // fp32 [pix][64] or null
   float scale2;          // v = v*scale2 + res2
@@ -92,9 +92,13 @@ struct ConvParams {
   float* out_f32_b;
   void* out_t;           // T output, pixel stride out_stride (elements), channel offset out_choff
   int out_stride, out_choff, out_rep;
+  int out_ps;            // 1: depth-to-space(2) store: the chunk's channels are ordered [sub-pixel s][c]; s -> (2y+s/2, 2x+s%2)
   F32Layout f32;         // layout of the fp32 trunk buffers (wpb == 0: plain [pixel][64])
   // final layer
   int final;
+  float final_scale;     // u8 = quantise(v * final_scale + final_add[c]); RRDBNet: 255, 0, truncating; EDSR: 1, mean, rounding
+  float final_add[3];
+  int final_round;
   uint8_t* out_u8;
   long long out_u8_pitch;
   float* out_img_f32;
@@ -119,9 +123,11 @@ __device__ __forceinline__ void epilogue_pixel(const ConvParams& P, int n, int y
 #pragma unroll
       for (int c = 0; c < 3; c++) {
         if (c < P.cout) {
-          float q = fminf(fmaxf(__fmul_rn(v[c], 255.0f), 0.0f), 255.0f);  // (out*255).clip(0,255).astype(u8)
-          P.out_u8[(long long)Y * P.out_u8_pitch + (long long)X * 3 + c] = (uint8_t)(int)q;
-          if (P.out_img_f32) P.out_img_f32[(long long)Y * P.out_img_f32_pitch + (long long)X * 3 + c] = v[c];
+          // RRDBNet: (out*255).clip(0,255).astype(u8) truncates (cnn_super_resolution.py:232)
+          const float f = __fadd_rn(__fmul_rn(v[c], P.final_scale), P.final_add[c]);
+          float q = fminf(fmaxf(f, 0.0f), 255.0f);
+          P.out_u8[(long long)Y * P.out_u8_pitch + (long long)X * 3 + c] = (uint8_t)(P.final_round ? __float2int_rn(q) : (int)q);
+          if (P.out_img_f32) P.out_img_f32[(long long)Y * P.out_img_f32_pitch + (long long)X * 3 + c] = P.final_round ? f : v[c];
         }
       }
     }
@@ -147,8 +153,9 @@ __device__ __forceinline__ void epilogue_pixel(const ConvParams& P, int n, int y
       for (int i = 0; i < NCH; i++) v[i] = __fadd_rn(__fmul_rn(v[i], P.scale2), t[i]);
     }
     if (P.act) {
+      const float slope = P.act == 1 ? 0.2f : 0.0f;
 #pragma unroll
-      for (int i = 0; i < NCH; i++) v[i] = v[i] >= 0.0f ? v[i] : __fmul_rn(v[i], 0.2f);
+      for (int i = 0; i < NCH; i++) v[i] = v[i] >= 0.0f ? v[i] : __fmul_rn(v[i], slope);
     }
     if (P.out_f32_a) {
       float* o = P.out_f32_a + fb;
@@ -184,8 +191,9 @@ __device__ __forceinline__ void epilogue_pixel(const ConvParams& P, int n, int y
       }
     }
     if (P.act) {
+      const float slope = P.act == 1 ? 0.2f : 0.0f;
 #pragma unroll
-      for (int i = 0; i < NCH; i++) v[i] = v[i] >= 0.0f ? v[i] : __fmul_rn(v[i], 0.2f);
+      for (int i = 0; i < NCH; i++) v[i] = v[i] >= 0.0f ? v[i] : __fmul_rn(v[i], slope);
     }
     if (P.out_f32_a) {
       float4* o = reinterpret_cast<float4*>(P.out_f32_a + pix * 64 + ch0);
@@ -212,6 +220,21 @@ __device__ __forceinline__ void epilogue_pixel(const ConvParams& P, int n, int y
         __nv_bfloat162 bb = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
         pk[i] = *reinterpret_cast<uint32_t*>(&bb);
       }
+    }
+    if (P.out_ps) {
+      // depth-to-space: 8 channels (16 B) per sub-pixel in this 32-channel chunk
+      static_assert(NCH == 32 || NCH == 16, "");
+      if constexpr (NCH == 32) {
+#pragma unroll
+        for (int sidx = 0; sidx < 2; sidx++) {
+          const int sp = (ch0 >> 4) + sidx;  // sub-pixel index 0..3 (16 channels each within a 64-channel group)
+          long long opix = ((long long)n * (P.h * 2) + (y * 2 + (sp >> 1))) * (P.w * 2) + (x * 2 + (sp & 1));
+          uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(P.out_t) + opix * P.out_stride + P.out_choff);
+          o[0] = make_uint4(pk[8 * sidx], pk[8 * sidx + 1], pk[8 * sidx + 2], pk[8 * sidx + 3]);
+          o[1] = make_uint4(pk[8 * sidx + 4], pk[8 * sidx + 5], pk[8 * sidx + 6], pk[8 * sidx + 7]);
+        }
+      }
+      return;
     }
     const int rep = P.out_rep;
     for (int dy = 0; dy < rep; dy++)

@@ -157,3 +157,23 @@ def test_upsampler_surface(ws):
     full = ws.app.wow_sr.wow_sr_array(rgb, up, enhance_crops=True)
     sr_rgb = np.ascontiguousarray(up.enhance(np.ascontiguousarray(rgb[:, :, ::-1]))[:, :, ::-1])
     assert np.array_equal(full, ws.app.wow_sr._enhance_for_crops(sr_rgb))
+
+
+@pytest.mark.parametrize("shape", [(40, 56), (150, 276)])
+def test_edsr_baseline_x4_self_consistency(ws, shape):
+    """EDSR-baseline x4 (BASELINE config 3).  PARITY UNPINNED: the oracle is our own restatement (oracle/edsr_ref.py)."""
+    from oracle import edsr_ref as E
+    importlib = __import__("importlib")
+    sr_mod = importlib.import_module("sentinel2-super-resolution-poc_b200.app.super_resolution")
+    sd = E.random_init_state_dict(0, 16)
+    sr, scale = sr_mod.create_sr_model(4, "edsr", state_dict=sd)
+    assert scale == 4
+    img = np.random.default_rng(2).integers(0, 256, shape + (3,), dtype=np.uint8)
+    out, f = sr.upsample_float(img)
+    ref_f = E.forward_float(sd, img, 16)
+    assert out.shape == (4 * shape[0], 4 * shape[1], 3)
+    w1, psnr, mx = _metrics(out, E.quantise(ref_f))
+    print("edsr parity", w1, psnr, mx, float(np.abs(f - ref_f).max()))
+    assert w1 >= 0.999 and psnr >= 50.0, (w1, psnr, mx)
+    with pytest.raises(ValueError):
+        sr_mod.create_sr_model(2, "espcn", state_dict=sd)
