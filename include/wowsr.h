@@ -178,6 +178,9 @@ int wowsr_conv3x3_host(wowsr_ctx* ctx, const float* in, int32_t n, int32_t h, in
 /* Timing of the last forward (CUDA events on the handle's stream): milliseconds per phase.
  * phases: 0 total, 1 head, 2 trunk (RRDBs), 3 tail (HR convs). Returns count written. */
 int32_t wowsr_get_timing(const wowsr_ctx* ctx, float* ms, int32_t cap);
+/* Debug: per-tile clock64 stamps [tile][mma_start, mma_issued, epilogue_start, epilogue_end] of CTA 0 of the conv
+ * launch selected with wowsr_set_option("tc_trace_layer", k) (k = 1-based launch index). Returns count. */
+int32_t wowsr_debug_trace(wowsr_ctx* ctx, int64_t* out, int32_t cap);
 
 /* ------------------------------------------------------------------------------------------ */
 /* EDSR-baseline x4 "farm SR" variant (super_resolution.py:92-124,196: cv2.dnn_superres          */

@@ -63,6 +63,7 @@ _SIGS = {
     "wowsr_conv3x3_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                      C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "wowsr_get_timing": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float), C.c_int32]),
+    "wowsr_debug_trace": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
     "wowsr_load_edsr": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.POINTER(C.c_void_p), C.c_int32, C.c_int32]),
     "wowsr_edsr_upsample_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
 }
@@ -132,6 +133,11 @@ class Handle:
         buf = (C.c_float * 4)()
         n = self._L.wowsr_get_timing(self._h, buf, 4)
         return dict(zip(("total", "head", "trunk", "tail"), list(buf)[:n]))
+
+    def debug_trace(self):
+        buf = (C.c_int64 * 256)()
+        n = self._L.wowsr_debug_trace(self._h, buf, 256)
+        return np.array(list(buf)[:max(n, 0)], dtype=np.int64).reshape(-1, 4)
 
     # -- post-process -------------------------------------------------------------------------
     def post_process_host(self, img: np.ndarray, params: PostParams) -> np.ndarray:

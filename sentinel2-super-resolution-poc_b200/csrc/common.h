@@ -46,6 +46,8 @@ struct wowsr_ctx {
   ConvNet* net = nullptr;
   ConvNet* edsr = nullptr;
   DevBuf img_in, img_out, img_out_f32;
+  DevBuf trace_buf;
+  int64_t trace_counter = 0;
   float timing[8] = {0};
   cudaEvent_t ev[8] = {nullptr};
 };

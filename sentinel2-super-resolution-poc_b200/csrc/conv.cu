@@ -238,6 +238,15 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
   P.final = io.final; P.out_u8 = io.out_u8; P.out_u8_pitch = io.out_u8_pitch;
   P.out_img_f32 = io.out_img_f32; P.out_img_f32_pitch = io.out_img_f32_pitch; P.wins = io.wins;
   P.err_flag = (int*)net->err.p;
+  P.trace = nullptr;
+  {  // debug tracing of one launch: option tc_trace_layer = 1-based index of the conv launch to trace
+    int64_t tl = wowsr_opt(ctx, "tc_trace_layer", 0);
+    if (tl > 0 && ++ctx->trace_counter == tl) {
+      if (int e = wowsr_ensure(ctx, ctx->trace_buf, 64 * 4 * 8)) return e;
+      cudaMemsetAsync(ctx->trace_buf.p, 0, 64 * 4 * 8, st);
+      P.trace = (long long*)ctx->trace_buf.p;
+    }
+  }
 
   if (wowsr_opt(ctx, "conv_impl", 0) == 1) {
     long long total = (long long)io.Nw * io.h * io.w;
@@ -545,6 +554,15 @@ extern "C" int wowsr_enhance_host(wowsr_ctx* ctx, const uint8_t* img_host, int32
   if (out_f32_host) WCUDA(ctx, cudaMemcpyAsync(out_f32_host, ctx->img_out_f32.p, out_bytes * 4, cudaMemcpyDeviceToHost, 0));
   WCUDA(ctx, cudaStreamSynchronize(0));
   return WOWSR_OK;
+}
+
+extern "C" int32_t wowsr_debug_trace(wowsr_ctx* ctx, int64_t* out, int32_t cap) {
+  if (!ctx || !out || !ctx->trace_buf.p) return WOWSR_ERR_ARG;
+  DeviceGuard g(ctx->device);
+  int n = cap < 256 ? cap : 256;
+  if (cudaMemcpy(out, ctx->trace_buf.p, (size_t)n * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return WOWSR_ERR_CUDA;
+  ctx->trace_counter = 0;
+  return n;
 }
 
 extern "C" int32_t wowsr_get_timing(const wowsr_ctx* ctx, float* ms, int32_t cap) {
