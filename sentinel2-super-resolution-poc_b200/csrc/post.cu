@@ -151,7 +151,7 @@ clahe_lut_kernel(const uint32_t* __restrict__ hist, int clip_limit, float lut_sc
 // pass B
 // ---------------------------------------------------------------------------------------------
 
-constexpr int PB_TX = 64, PB_TY = 64, PB_THREADS = 256, PB_MAXR = 8;
+constexpr int PB_TX = 64, PB_TY = 64, PB_THREADS = 512, PB_MAXR = 8;
 
 struct PostK {
   int stages;
@@ -287,6 +287,7 @@ post_apply_kernel(ImgView img, OutView out, const WowsrTables* __restrict__ tabs
     const int bx = (tile % tiles_x) * PB_TX;
     const int by = row0 + (tile / tiles_x) * PB_TY;
     // stage 1: enhanced RGB for the halo tile (reflect-101 at the image borders)
+#pragma unroll 2
     for (int i = tid; i < EH * EW; i += PB_THREADS) {
       int ey = i / EW, ex = i - ey * EW;
       int gx = reflect101(bx - r + ex, img.W), gy = reflect101(by - r + ey, img.H);
@@ -304,6 +305,7 @@ post_apply_kernel(ImgView img, OutView out, const WowsrTables* __restrict__ tabs
     __syncthreads();
     if (k.stages & WOWSR_STAGE_UNSHARP) {
       // stage 2: horizontal pass, exact in u16
+#pragma unroll 2
       for (int i = tid; i < EH * PB_TX; i += PB_THREADS) {
         int ey = i / PB_TX, x = i - ey * PB_TX;
         const uint32_t* e = E + ey * EW + x;
@@ -320,6 +322,7 @@ post_apply_kernel(ImgView img, OutView out, const WowsrTables* __restrict__ tabs
       __syncthreads();
     }
     // stage 3: vertical pass + unsharp + vegetation, one pixel per thread iteration
+#pragma unroll 2
     for (int i = tid; i < PB_TX * PB_TY; i += PB_THREADS) {
       int y = i / PB_TX, x = i - y * PB_TX;
       int gx = bx + x, gy = by + y;

@@ -97,3 +97,37 @@ def test_idempotent_launch_and_error_paths(ws, handle):
         handle.post_process_host(img[..., 0], ws._lib.post_params("wow"))
     with pytest.raises(ws.WowsrError):
         handle.post_process_host(img, ws._lib.post_params("wow", sigma=9.0))
+
+
+@pytest.mark.parametrize("shape", [(8, 8), (9, 9), (1, 40), (40, 1), (33, 31)])
+def test_tiny_and_degenerate_shapes(ws, handle, shape):
+    """Smaller than the CLAHE grid / blur radius: reflect-101 folds several times, tiles are 1-2 pixels."""
+    img = image_like(max(shape[0], 16), max(shape[1], 16), seed=shape[0] + 3)[:shape[0], :shape[1]].copy()
+    try:
+        want = wow_cv2.enhance_for_crops(img)
+    except Exception:
+        pytest.skip("cv2 rejects this shape")
+    assert np.array_equal(handle.post_process_host(img, ws._lib.post_params("wow")), want)
+
+
+def test_constant_and_extreme_images(ws, handle):
+    for val in (0, 255, 128):
+        img = np.full((128, 96, 3), val, np.uint8)
+        assert np.array_equal(handle.post_process_host(img, ws._lib.post_params("wow")), wow_cv2.enhance_for_crops(img))
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (257, 263, 3), dtype=np.uint8)          # white noise: every LUT bin populated
+    assert np.array_equal(handle.post_process_host(img, ws._lib.post_params("farm")), wow_cv2.farm_post(img))
+
+
+def test_full_size_properties_4096(ws, handle):
+    """BASELINE config 4 size (4096x4096): histogram mass conservation, determinism, and agreement with cv2."""
+    import torch
+    img = np.tile(image_like(1024, 1024, seed=3), (4, 4, 1))
+    d = torch.from_numpy(img).cuda()
+    hist = torch.zeros(64 * 256, dtype=torch.int32, device="cuda")
+    handle.clahe_hist(ws._lib.Image(d.data_ptr(), 4096 * 3, 4096, 4096, 0, 4096), 8, 0, 4096, hist.data_ptr())
+    torch.cuda.synchronize()
+    assert int(hist.sum()) == 4096 * 4096 and (hist.view(64, 256).sum(1) == 512 * 512).all()
+    a = handle.post_process_host(img, ws._lib.post_params("wow"))
+    assert np.array_equal(a, handle.post_process_host(img, ws._lib.post_params("wow")))
+    assert np.array_equal(a, wow_cv2.enhance_for_crops(img))

@@ -177,3 +177,47 @@ def test_edsr_baseline_x4_self_consistency(ws, shape):
     assert w1 >= 0.999 and psnr >= 50.0, (w1, psnr, mx)
     with pytest.raises(ValueError):
         sr_mod.create_sr_model(2, "espcn", state_dict=sd)
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (3, 5), (8, 300), (129, 2), (16, 16)])
+def test_rrdbnet_ragged_and_tiny_inputs(ws, handle, shape):
+    """Edge shapes: smaller than a run, a single pixel, one-pixel-wide strips (TMA boxes larger than the tensor)."""
+    blocks = 1
+    sd = R.calibrate_conv_last(R.random_init_state_dict(3, blocks), blocks)
+    handle.load_rrdbnet(_tensors(sd, blocks), blocks, precision="bf16")
+    img = np.random.default_rng(shape[0] * 31 + shape[1]).integers(0, 256, shape + (3,), dtype=np.uint8)
+    u8, f = handle.enhance_host(img, 256, want_float=True)
+    ref_f = R.enhance_float(sd, img, blocks, 256)
+    assert u8.shape == (4 * shape[0], 4 * shape[1], 3)
+    d = np.abs(u8.astype(int) - R.quantise(ref_f).astype(int))
+    assert (d <= 1).mean() >= 0.999 and d.max() <= 2, (shape, float((d <= 1).mean()), int(d.max()))
+    assert np.abs(f - ref_f).max() < 0.02 * max(1.0, np.abs(ref_f).max())
+
+
+def test_window_independence_and_determinism(ws, handle):
+    """Size-independent properties of the tiled path (cnn_super_resolution.py:236-280) at a multi-window size:
+    (1) two runs are bit-identical; (2) the pixels a window owns depend only on that window's LR pixels —
+    changing the image outside a window must not change what the window writes."""
+    blocks = 2
+    sd = R.calibrate_conv_last(R.random_init_state_dict(1, blocks), blocks)
+    handle.load_rrdbnet(_tensors(sd, blocks), blocks, precision="bf16")
+    rng = np.random.default_rng(9)
+    H, W, T = 600, 700, 256
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    a = handle.enhance_host(img, T)
+    b = handle.enhance_host(img, T)
+    assert np.array_equal(a, b)
+    wins = ws._lib.plan_windows(H, W, T)
+    assert len(wins) == 9
+    w = wins[4]                                       # centre window
+    img2 = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    img2[w.y0:w.y1, w.x0:w.x1] = img[w.y0:w.y1, w.x0:w.x1]
+    c = handle.enhance_host(img2, T)
+    ys, xs = slice(4 * w.oy0, 4 * w.oy1), slice(4 * w.ox0, 4 * w.ox1)
+    assert np.array_equal(a[ys, xs], c[ys, xs])
+    assert not np.array_equal(a, c)
+    # the owned rectangles tile the output exactly once
+    cover = np.zeros((4 * H, 4 * W), np.int32)
+    for q in wins:
+        cover[4 * q.oy0:4 * q.oy1, 4 * q.ox0:4 * q.ox1] += 1
+    assert (cover == 1).all()
