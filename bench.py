@@ -163,16 +163,19 @@ def run_reference(args):
         return
     wl = workload(args.workload, args.gpus)
     vals = []
+    times = []
     t_start = time.perf_counter()
     for i in range(args.warmup + args.steps):
         # each step = one bounded sample; on slow hosts shrink the sample so the whole run stays within minutes
         px = (448, 448) if time.perf_counter() - t_start < 60 else (128, 128)
+        t_s = time.perf_counter()
         v, desc, cores = cpu_sample(wl, sample_px=px if args.workload != "post4096" else (1024, 1024))
         if i >= args.warmup:
             vals.append(v)
+            times.append((time.perf_counter() - t_s) * 1e3)
     value = sum(vals) / len(vals)
     line = {"impl": "reference", "metric": "output Mpix/s (x4 RRDBNet + WOW post-process)", "value": value, "unit": "Mpix/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sum(times) / len(times), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["label"], "note": "oracle port of the reference CPU path (torch fp32 + cv2); each step = one bounded sample"},
             "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": desc},
