@@ -312,10 +312,18 @@ def run_ours(args):
         conv_t = sum(conv_ms) / len(conv_ms) / 1e3
         per_rank_flops = flops / world
         ach = per_rank_flops / conv_t / 1e12
+        traffic = None
+        try:  # dram__bytes_read+write of the 350 launches from the committed ncu pass (9 windows of 532x532), scaled by window pixels
+            with open(os.path.join(ROOT, "profiles", "r01_cfg2s_dram_traffic.json")) as f:
+                t = json.load(f)
+            traffic = t["dram_bytes"] / (t["windows"] * 532 * 532) * (flops / world / FLOP_PER_LR_PX)
+        except Exception:  # noqa: BLE001
+            pass
         roof = {"bound": "tensor", "kernel": "conv3x3_tc_kernel (all 350 launches of a step, rank 0)", "achieved": ach,
                 "peak": pk["bf16_tflops_sustained"], "peak_burst": pk["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": ach / pk["bf16_tflops_sustained"], "frac_of_burst": ach / pk["bf16_tflops"], "peak_source": pk["src"],
-                "traffic": None, "conv_ms_per_step": conv_t * 1e3, "algorithmic_flops_per_step": per_rank_flops}
+                "traffic": traffic, "traffic_note": "DRAM bytes per step of these launches (ncu, profiles/r01_cfg2s_dram_traffic.json, scaled per window pixel)",
+                "conv_ms_per_step": conv_t * 1e3, "algorithmic_flops_per_step": per_rank_flops}
     else:
         ach = OH * OW * POST_BYTES_PER_PX / (ms / 1e3) / 1e9
         roof = {"bound": "hbm", "kernel": "clahe_hist + post_apply", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
