@@ -47,7 +47,7 @@ constexpr int HIST_THREADS = 256;
 
 __global__ void __launch_bounds__(HIST_THREADS)
 clahe_hist_kernel(ImgView img, const WowsrTables* __restrict__ tabs, int grid, int tw, int th, int prow0, int prow1,
-                  int rows_per_block, int chunks_per_tile, int vec_ok, uint32_t* __restrict__ hist) {
+                  int rows_per_block, int chunks_per_tile, int vec_ok, int use_match, uint32_t* __restrict__ hist) {
   __shared__ uint16_t s_gam[256];
   __shared__ uint16_t s_cbrt[3072];
   __shared__ uint32_t s_h[HIST_THREADS / 32][256];
@@ -92,9 +92,19 @@ clahe_hist_kernel(ImgView img, const WowsrTables* __restrict__ tabs, int grid, i
     }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
+      // warp-aggregated update: a warp whose 32 lanes fall in one bin (flat or clipped regions) issues ONE atomic
+      // of 32; mixed warps use plain per-lane shared atomics.  Full __match_any_sync grouping (option
+      // hist_match=1) measured 2.6x slower on image-like data: the match costs more than the replays it saves.
       uint32_t bin = bins[k];
-      unsigned m = __match_any_sync(0xFFFFFFFFu, bin);
-      if (bin != 0xFFFFFFFFu && lane == __ffs(m) - 1) atomicAdd(&s_h[warp][bin], (uint32_t)__popc(m));
+      const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, bin, 0);
+      if (__all_sync(0xFFFFFFFFu, bin == b0)) {
+        if (lane == 0 && bin != 0xFFFFFFFFu) atomicAdd(&s_h[warp][bin], 32u);
+      } else if (use_match) {
+        unsigned m = __match_any_sync(0xFFFFFFFFu, bin);
+        if (bin != 0xFFFFFFFFu && lane == __ffs(m) - 1) atomicAdd(&s_h[warp][bin], (uint32_t)__popc(m));
+      } else if (bin != 0xFFFFFFFFu) {
+        atomicAdd(&s_h[warp][bin], 1u);
+      }
     }
   }
   __syncthreads();
@@ -184,45 +194,6 @@ __device__ __forceinline__ int ab2xz(int i) {
 
 __device__ __forceinline__ int ds(int x, int n) { return (x + (1 << (n - 1))) >> n; }
 
-// CLAHE + Lab round trip for one pixel at image position (x, y): returns packed r | g<<8 | b<<16
-__device__ __forceinline__ uint32_t enhance_pixel(int r, int g, int b, int x, int y, const PostK& k,
-                                                  const SmemTabs& T, const uint8_t* __restrict__ luts) {
-  // RGB -> Lab (A.1)
-  int R = T.gam[r], G = T.gam[g], B = T.gam[b];
-  int fX = T.cbrt[ds(1777 * R + 1541 * G + 778 * B, 12)];
-  int fY = T.cbrt[ds(871 * R + 2929 * G + 296 * B, 12)];
-  int fZ = T.cbrt[ds(73 * R + 448 * G + 3575 * B, 12)];
-  int L = clampi(ds(296 * fY - 1336934, 15), 0, 255);
-  int a = clampi(ds(500 * (fX - fY) + 128 * 32768, 15), 0, 255);
-  int bb = clampi(ds(200 * (fY - fZ) + 128 * 32768, 15), 0, 255);
-  // CLAHE bilinear LUT interpolation (A.2), fp32 with separately rounded operations
-  float txf = __fsub_rn(__fmul_rn((float)x, k.inv_tw), 0.5f);
-  float tyf = __fsub_rn(__fmul_rn((float)y, k.inv_th), 0.5f);
-  int tx1 = (int)floorf(txf), ty1 = (int)floorf(tyf);
-  float xa = __fsub_rn(txf, (float)tx1), ya = __fsub_rn(tyf, (float)ty1);
-  float xa1 = __fsub_rn(1.0f, xa), ya1 = __fsub_rn(1.0f, ya);
-  int tx2 = min(tx1 + 1, k.grid - 1), ty2 = min(ty1 + 1, k.grid - 1);
-  tx1 = max(tx1, 0);
-  ty1 = max(ty1, 0);
-  float p00 = (float)__ldg(luts + ((ty1 * k.grid + tx1) << 8) + L);
-  float p01 = (float)__ldg(luts + ((ty1 * k.grid + tx2) << 8) + L);
-  float p10 = (float)__ldg(luts + ((ty2 * k.grid + tx1) << 8) + L);
-  float p11 = (float)__ldg(luts + ((ty2 * k.grid + tx2) << 8) + L);
-  float top = __fadd_rn(__fmul_rn(p00, xa1), __fmul_rn(p01, xa));
-  float bot = __fadd_rn(__fmul_rn(p10, xa1), __fmul_rn(p11, xa));
-  float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
-  L = clampi(__float2int_rn(res), 0, 255);
-  // Lab -> RGB (A.3)
-  int yy = T.lab_y[L], ify = T.lab_ify[L];
-  int adiv = ((5 * a * 53687 + 128) >> 13) - 4194;
-  int bdiv = ((bb * 41943 + 16) >> 9) - 10485 + 1;
-  int X = ab2xz(ify + adiv), Z = ab2xz(ify - bdiv);
-  int ro = clampi(ds(12615 * X - 6296 * yy - 2223 * Z, 14), 0, 4095);
-  int go = clampi(ds(-3773 * X + 7684 * yy + 185 * Z, 14), 0, 4095);
-  int bo = clampi(ds(217 * X - 836 * yy + 4715 * Z, 14), 0, 4095);
-  return (uint32_t)T.invgam[ro] | ((uint32_t)T.invgam[go] << 8) | ((uint32_t)T.invgam[bo] << 16);
-}
-
 // RGB -> HSV -> green boost -> HSV -> RGB (A.6 + glue wow_sr.py:200-207)
 __device__ __forceinline__ uint32_t vegetation_pixel(int r, int g, int b, bool tail, const PostK& k, const SmemTabs& T) {
   int v = max(max(r, g), b), mn = min(min(r, g), b);
@@ -267,88 +238,158 @@ __device__ __forceinline__ uint32_t vegetation_pixel(int r, int g, int b, bool t
   return (uint32_t)clampi(ri, 0, 255) | ((uint32_t)clampi(gi, 0, 255) << 8) | ((uint32_t)clampi(bi, 0, 255) << 16);
 }
 
+// RAD = blur radius (compile time: the tap loops unroll and the halo geometry is constant).  Work split:
+// one warp per tile row, lanes over columns, so everything that depends only on the row (source row pointer,
+// CLAHE y-interpolation, LUT rows) or only on the column (reflected x, x-interpolation) is hoisted out of the
+// per-pixel path; the kernel is instruction-issue bound, not HBM bound.
+template <int RAD>
 __global__ void __launch_bounds__(PB_THREADS)
 post_apply_kernel(ImgView img, OutView out, const WowsrTables* __restrict__ tabs, const uint8_t* __restrict__ luts,
                   PostK k, int row0, int row1, int tiles_x, int n_tiles) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   SmemTabs& T = *reinterpret_cast<SmemTabs*>(smem_raw);
-  const int r = k.r;
-  const int EW = PB_TX + 2 * r, EH = PB_TY + 2 * r;
+  constexpr int r = RAD;
+  constexpr int EW = PB_TX + 2 * r, EH = PB_TY + 2 * r;
+  constexpr int NCOL = (EW + 31) / 32;  // columns of the halo tile per lane
+  constexpr int NWARP = PB_THREADS / 32;
   uint32_t* E = reinterpret_cast<uint32_t*>(smem_raw + ((sizeof(SmemTabs) + 15) & ~15));  // [EH][EW] packed rgb
   uint2* Hs = reinterpret_cast<uint2*>(E + EH * EW + ((EH * EW) & 1));                    // [EH][PB_TX] 3 x u16 (+pad)
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(tabs);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&T);
     for (int i = tid; i < (int)(sizeof(SmemTabs) / 4); i += PB_THREADS) dst[i] = __ldg(src + i);
   }
   __syncthreads();
+  const bool do_clahe = k.stages & WOWSR_STAGE_CLAHE;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int bx = (tile % tiles_x) * PB_TX;
     const int by = row0 + (tile / tiles_x) * PB_TY;
-    // stage 1: enhanced RGB for the halo tile (reflect-101 at the image borders)
-#pragma unroll 2
-    for (int i = tid; i < EH * EW; i += PB_THREADS) {
-      int ey = i / EW, ex = i - ey * EW;
-      int gx = reflect101(bx - r + ex, img.W), gy = reflect101(by - r + ey, img.H);
-      int gyb = gy - img.y0;
+    // ---- per-column constants of this tile (registers) ----
+    int goff[NCOL], ctx1[NCOL], ctx2[NCOL];
+    float cxa[NCOL], cxa1[NCOL];
+#pragma unroll
+    for (int c = 0; c < NCOL; c++) {
+      const int ex = lane + 32 * c;
+      const int gx = reflect101(bx - r + (ex < EW ? ex : 0), img.W);
+      goff[c] = gx * 3;
+      const float txf = __fsub_rn(__fmul_rn((float)gx, k.inv_tw), 0.5f);
+      const int t1 = (int)floorf(txf);
+      cxa[c] = __fsub_rn(txf, (float)t1);
+      cxa1[c] = __fsub_rn(1.0f, cxa[c]);
+      ctx2[c] = min(t1 + 1, k.grid - 1) << 8;
+      ctx1[c] = max(t1, 0) << 8;
+    }
+    // ---- stage 1: enhanced RGB for the halo tile (reflect-101 at the image borders) ----
+    for (int ey = warp; ey < EH; ey += NWARP) {
+      const int gy = reflect101(by - r + ey, img.H);
+      const int gyb = gy - img.y0;
+      uint32_t* erow = E + ey * EW;
       if (gyb < 0 || gyb >= img.rows) {  // tile overhang beyond the band: never consumed
-        E[i] = 0;
+#pragma unroll
+        for (int c = 0; c < NCOL; c++)
+          if (lane + 32 * c < EW) erow[lane + 32 * c] = 0;
         continue;
       }
-      const uint8_t* p = img.data + (long long)gyb * img.pitch + gx * 3;
-      int cr = __ldg(p), cg = __ldg(p + 1), cb = __ldg(p + 2);
-      uint32_t e = (k.stages & WOWSR_STAGE_CLAHE) ? enhance_pixel(cr, cg, cb, gx, gy, k, T, luts)
-                                                  : ((uint32_t)cr | ((uint32_t)cg << 8) | ((uint32_t)cb << 16));
-      E[i] = e;
+      const uint8_t* rp = img.data + (long long)gyb * img.pitch;
+      const float tyf = __fsub_rn(__fmul_rn((float)gy, k.inv_th), 0.5f);
+      const int t1 = (int)floorf(tyf);
+      const float ya = __fsub_rn(tyf, (float)t1), ya1 = __fsub_rn(1.0f, ya);
+      const uint8_t* lut1 = luts + ((max(t1, 0) * k.grid) << 8);
+      const uint8_t* lut2 = luts + ((min(t1 + 1, k.grid - 1) * k.grid) << 8);
+#pragma unroll
+      for (int c = 0; c < NCOL; c++) {
+        const int ex = lane + 32 * c;
+        if (ex >= EW) break;
+        const uint8_t* p = rp + goff[c];
+        const int cr = __ldg(p), cg = __ldg(p + 1), cb = __ldg(p + 2);
+        uint32_t e;
+        if (do_clahe) {
+          // RGB -> Lab (A.1)
+          const int R = T.gam[cr], G = T.gam[cg], B = T.gam[cb];
+          const int fX = T.cbrt[ds(1777 * R + 1541 * G + 778 * B, 12)];
+          const int fY = T.cbrt[ds(871 * R + 2929 * G + 296 * B, 12)];
+          const int fZ = T.cbrt[ds(73 * R + 448 * G + 3575 * B, 12)];
+          int L = clampi(ds(296 * fY - 1336934, 15), 0, 255);
+          const int a = clampi(ds(500 * (fX - fY) + 128 * 32768, 15), 0, 255);
+          const int bb = clampi(ds(200 * (fY - fZ) + 128 * 32768, 15), 0, 255);
+          // CLAHE bilinear LUT interpolation (A.2): fp32, every multiply and add rounded separately
+          const float p00 = (float)__ldg(lut1 + ctx1[c] + L), p01 = (float)__ldg(lut1 + ctx2[c] + L);
+          const float p10 = (float)__ldg(lut2 + ctx1[c] + L), p11 = (float)__ldg(lut2 + ctx2[c] + L);
+          const float top = __fadd_rn(__fmul_rn(p00, cxa1[c]), __fmul_rn(p01, cxa[c]));
+          const float bot = __fadd_rn(__fmul_rn(p10, cxa1[c]), __fmul_rn(p11, cxa[c]));
+          L = clampi(__float2int_rn(__fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya))), 0, 255);
+          // Lab -> RGB (A.3)
+          const int yy = T.lab_y[L], ify = T.lab_ify[L];
+          const int adiv = ((5 * a * 53687 + 128) >> 13) - 4194;
+          const int bdiv = ((bb * 41943 + 16) >> 9) - 10485 + 1;
+          const int X = ab2xz(ify + adiv), Z = ab2xz(ify - bdiv);
+          const int ro = clampi(ds(12615 * X - 6296 * yy - 2223 * Z, 14), 0, 4095);
+          const int go = clampi(ds(-3773 * X + 7684 * yy + 185 * Z, 14), 0, 4095);
+          const int bo = clampi(ds(217 * X - 836 * yy + 4715 * Z, 14), 0, 4095);
+          e = (uint32_t)T.invgam[ro] | ((uint32_t)T.invgam[go] << 8) | ((uint32_t)T.invgam[bo] << 16);
+        } else {
+          e = (uint32_t)cr | ((uint32_t)cg << 8) | ((uint32_t)cb << 16);
+        }
+        erow[ex] = e;
+      }
     }
     __syncthreads();
-    if (k.stages & WOWSR_STAGE_UNSHARP) {
-      // stage 2: horizontal pass, exact in u16
-#pragma unroll 2
-      for (int i = tid; i < EH * PB_TX; i += PB_THREADS) {
-        int ey = i / PB_TX, x = i - ey * PB_TX;
-        const uint32_t* e = E + ey * EW + x;
-        uint32_t ar = 0, ag = 0, ab = 0;
-        for (int t = 0; t <= 2 * r; t++) {
-          uint32_t px = e[t];
-          uint32_t w = k.taps[t];
-          ar += w * (px & 255);
-          ag += w * ((px >> 8) & 255);
-          ab += w * ((px >> 16) & 255);
+    if (r > 0) {
+      // ---- stage 2: horizontal pass, exact in u16 ----
+      for (int ey = warp; ey < EH; ey += NWARP) {
+#pragma unroll
+        for (int c = 0; c < PB_TX / 32; c++) {
+          const int x = lane + 32 * c;
+          const uint32_t* e = E + ey * EW + x;
+          uint32_t ar = 0, ag = 0, ab = 0;
+#pragma unroll
+          for (int t = 0; t <= 2 * r; t++) {
+            const uint32_t px = e[t];
+            const uint32_t w = k.taps[t];
+            ar += w * (px & 255);
+            ag += w * ((px >> 8) & 255);
+            ab += w * ((px >> 16) & 255);
+          }
+          Hs[ey * PB_TX + x] = make_uint2(ar | (ag << 16), ab);
         }
-        Hs[i] = make_uint2(ar | (ag << 16), ab);
       }
       __syncthreads();
     }
-    // stage 3: vertical pass + unsharp + vegetation, one pixel per thread iteration
-#pragma unroll 2
-    for (int i = tid; i < PB_TX * PB_TY; i += PB_THREADS) {
-      int y = i / PB_TX, x = i - y * PB_TX;
-      int gx = bx + x, gy = by + y;
-      if (gx >= img.W || gy >= row1) continue;
-      uint32_t e = E[(y + r) * EW + x + r];
-      int cr = e & 255, cg = (e >> 8) & 255, cb = (e >> 16) & 255;
-      if (k.stages & WOWSR_STAGE_UNSHARP) {
-        uint32_t ar = 0, ag = 0, ab = 0;
-        for (int t = 0; t <= 2 * r; t++) {
-          uint2 hv = Hs[(y + t) * PB_TX + x];
-          uint32_t w = k.taps[t];
-          ar += w * (hv.x & 0xFFFF);
-          ag += w * (hv.x >> 16);
-          ab += w * (hv.y & 0xFFFF);
+    // ---- stage 3: vertical pass + unsharp + vegetation ----
+    for (int y = warp; y < PB_TY; y += NWARP) {
+      const int gy = by + y;
+      if (gy >= row1) break;
+      uint8_t* orow = out.data + (long long)(gy - out.y0) * out.pitch;
+#pragma unroll
+      for (int c = 0; c < PB_TX / 32; c++) {
+        const int x = lane + 32 * c;
+        const int gx = bx + x;
+        if (gx >= img.W) continue;
+        const uint32_t e = E[(y + r) * EW + x + r];
+        int cr = e & 255, cg = (e >> 8) & 255, cb = (e >> 16) & 255;
+        if (r > 0) {
+          uint32_t ar = 0, ag = 0, ab = 0;
+#pragma unroll
+          for (int t = 0; t <= 2 * r; t++) {
+            const uint2 hv = Hs[(y + t) * PB_TX + x];
+            const uint32_t w = k.taps[t];
+            ar += w * (hv.x & 0xFFFF);
+            ag += w * (hv.x >> 16);
+            ab += w * (hv.y & 0xFFFF);
+          }
+          const int br = (ar + 32768) >> 16, bg = (ag + 32768) >> 16, bb = (ab + 32768) >> 16;
+          cr = clampi(__float2int_rn(__fadd_rn(__fmul_rn((float)cr, k.alpha), __fmul_rn((float)br, k.beta))), 0, 255);
+          cg = clampi(__float2int_rn(__fadd_rn(__fmul_rn((float)cg, k.alpha), __fmul_rn((float)bg, k.beta))), 0, 255);
+          cb = clampi(__float2int_rn(__fadd_rn(__fmul_rn((float)cb, k.alpha), __fmul_rn((float)bb, k.beta))), 0, 255);
         }
-        int br = (ar + 32768) >> 16, bg = (ag + 32768) >> 16, bb = (ab + 32768) >> 16;
-        cr = clampi(__float2int_rn(__fadd_rn(__fmul_rn((float)cr, k.alpha), __fmul_rn((float)br, k.beta))), 0, 255);
-        cg = clampi(__float2int_rn(__fadd_rn(__fmul_rn((float)cg, k.alpha), __fmul_rn((float)bg, k.beta))), 0, 255);
-        cb = clampi(__float2int_rn(__fadd_rn(__fmul_rn((float)cb, k.alpha), __fmul_rn((float)bb, k.beta))), 0, 255);
+        uint32_t o = (uint32_t)cr | ((uint32_t)cg << 8) | ((uint32_t)cb << 16);
+        if (k.stages & WOWSR_STAGE_VEG) o = vegetation_pixel(cr, cg, cb, gx >= k.tail_x, k, T);
+        uint8_t* q = orow + gx * 3;
+        q[0] = (uint8_t)(o & 255);
+        q[1] = (uint8_t)((o >> 8) & 255);
+        q[2] = (uint8_t)(o >> 16);
       }
-      uint32_t o = (uint32_t)cr | ((uint32_t)cg << 8) | ((uint32_t)cb << 16);
-      if (k.stages & WOWSR_STAGE_VEG) o = vegetation_pixel(cr, cg, cb, gx >= k.tail_x, k, T);
-      uint8_t* q = out.data + (long long)(gy - out.y0) * out.pitch + gx * 3;
-      q[0] = (uint8_t)(o & 255);
-      q[1] = (uint8_t)((o >> 8) & 255);
-      q[2] = (uint8_t)(o >> 16);
     }
     __syncthreads();
   }
@@ -400,7 +441,7 @@ extern "C" int wowsr_clahe_hist(wowsr_ctx* ctx, const wowsr_image* rgb, int32_t 
   int vec_ok = (rgb->pitch % 4 == 0) && (((uintptr_t)rgb->data) % 4 == 0) && (tw % 4 == 0);
   dim3 gr(grid, grid * chunks);
   clahe_hist_kernel<<<gr, HIST_THREADS, 0, (cudaStream_t)stream>>>(v, ctx->d_tables, grid, tw, th, prow0, prow1,
-                                                                    rows_per_block, chunks, vec_ok, hist_dev);
+                                                                    rows_per_block, chunks, vec_ok, (int)wowsr_opt(ctx, "hist_match", 0), hist_dev);
   WLAUNCH_CHECK(ctx);
   return WOWSR_OK;
 }
@@ -471,13 +512,29 @@ extern "C" int wowsr_post_apply(wowsr_ctx* ctx, const wowsr_image* rgb, const ui
   int n_tiles = tiles_x * tiles_y;
   size_t smem = post_smem_bytes(k.r);
   static_assert(sizeof(SmemTabs) == sizeof(WowsrTables), "table layouts must match");
-  WCUDA(ctx, cudaFuncSetAttribute(post_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = (int)(200 * 1024 / smem);
   if (per_sm < 1) per_sm = 1;
+  if (per_sm > 2048 / PB_THREADS) per_sm = 2048 / PB_THREADS;
   int blocks = ctx->sm_count * per_sm;
   if (blocks > n_tiles) blocks = n_tiles;
-  post_apply_kernel<<<blocks, PB_THREADS, smem, (cudaStream_t)stream>>>(iv, ov, ctx->d_tables, luts_dev, k, row0, row1,
-                                                                        tiles_x, n_tiles);
+#define WOWSR_POST_LAUNCH(RR)                                                                                          \
+  {                                                                                                                    \
+    WCUDA(ctx, cudaFuncSetAttribute(post_apply_kernel<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    post_apply_kernel<RR><<<blocks, PB_THREADS, smem, (cudaStream_t)stream>>>(iv, ov, ctx->d_tables, luts_dev, k, row0, \
+                                                                              row1, tiles_x, n_tiles);                 \
+  }
+  // the kernel is specialised on the halo radius; taps beyond the true radius are zero, so rounding r up is exact
+  const int true_r = k.r;
+  const int rr = true_r == 0 ? 0 : (true_r <= 3 ? 3 : (true_r <= 4 ? 4 : PB_MAXR));
+  if (rr != true_r) {  // re-centre the taps in the wider window
+    int tmp[2 * PB_MAXR + 1] = {0};
+    for (int t = 0; t <= 2 * true_r; t++) tmp[t + (rr - true_r)] = k.taps[t];
+    for (int t = 0; t <= 2 * rr; t++) k.taps[t] = tmp[t];
+    k.r = rr;  // rows the wider halo reads outside the band are zero-filled in the kernel and meet zero taps
+  }
+  smem = post_smem_bytes(rr);
+  if (rr == 0) WOWSR_POST_LAUNCH(0) else if (rr == 3) WOWSR_POST_LAUNCH(3) else if (rr == 4) WOWSR_POST_LAUNCH(4) else WOWSR_POST_LAUNCH(PB_MAXR)
+#undef WOWSR_POST_LAUNCH
   WLAUNCH_CHECK(ctx);
   return WOWSR_OK;
 }
