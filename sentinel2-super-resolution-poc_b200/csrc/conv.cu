@@ -94,8 +94,13 @@ int upload_layer(wowsr_ctx* ctx, LayerW& L, const float* w, const float* b, int 
           for (int ch = 0; ch < 64; ch++) {
             const int ci = c * 64 + ch;
             if (ci >= cin) break;
-            size_t off = (size_t)c * L.chunk_bytes + (size_t)a * (3 * N * 128) + (size_t)row * 128 +
-                         (size_t)(((ch >> 3) ^ (row & 7)) << 4) + (size_t)(ch & 7) * 2;
+            // full chunk: 128-byte rows, SWIZZLE_128B (16-byte unit index ^ row%8); 32-channel remainder chunk:
+            // 64-byte rows, SWIZZLE_64B (unit index ^ (row/2)%4) — the image the UMMA descriptors expect in smem
+            const bool half_c = cin - c * 64 < 64;
+            size_t off = half_c ? (size_t)c * L.chunk_bytes + (size_t)a * (3 * N * 64) + (size_t)row * 64 +
+                                      (size_t)(((ch >> 3) ^ ((row >> 1) & 3)) << 4) + (size_t)(ch & 7) * 2
+                                : (size_t)c * L.chunk_bytes + (size_t)a * (3 * N * 128) + (size_t)row * 128 +
+                                      (size_t)(((ch >> 3) ^ (row & 7)) << 4) + (size_t)(ch & 7) * 2;
             const uint16_t th = to_t(w[(((size_t)co * cin + ci) * 3 + b) * 3 + a], fp16);  // ky = b, kx = a
             const uint16_t tv = to_t(w[(((size_t)co * cin + ci) * 3 + a) * 3 + b], fp16);  // ky = a, kx = b
             memcpy(&pack[off], &th, 2);
@@ -150,7 +155,8 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 
 // 4-D map over an NHWC activation buffer: dims (C, W, H, N), box (64 ch, 130 px, 1 row, 1 window)
 // `transposed`: dims (C, H, W, N) — the run axis (box of 130) walks y; used by the vertical tiles.
-int make_tmap(wowsr_ctx* ctx, CUtensorMap* m, const void* base, int C, int W, int H, int Nw, bool fp16, bool transposed) {
+int make_tmap(wowsr_ctx* ctx, CUtensorMap* m, const void* base, int C, int W, int H, int Nw, bool fp16, bool transposed,
+              bool half = false) {
   auto enc = get_encode();
   if (!enc) return wowsr_fail(ctx, WOWSR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Nw};
@@ -161,10 +167,10 @@ int make_tmap(wowsr_ctx* ctx, CUtensorMap* m, const void* base, int C, int W, in
     strides[0] = (cuuint64_t)C * 2 * W;
     strides[1] = (cuuint64_t)C * 2;
   }
-  cuuint32_t box[4] = {64, (cuuint32_t)TC_AROWS, 2, 1};  // one pipeline stage = two consecutive rows of the row axis
+  cuuint32_t box[4] = {half ? 32u : 64u, (cuuint32_t)TC_AROWS, 2, 1};  // one pipeline stage = two consecutive rows of the row axis
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base),
-                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, half ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return wowsr_fail(ctx, WOWSR_ERR_CUDA, "cuTensorMapEncodeTiled(C=%d,W=%d,H=%d,N=%d) -> CUresult %d", C, W, H, Nw, (int)r);
@@ -258,9 +264,14 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
     WLAUNCH_CHECK(ctx);
     return 0;
   }
-  CUtensorMap tmap, tmap_v;
+  CUtensorMap tmap, tmap_v, tmap32, tmap_v32;
   if (int e = make_tmap(ctx, &tmap, io.in, io.in_C, io.w, io.h, io.Nw, L.fp16, false)) return e;
   tmap_v = tmap;
+  const bool has_half = L.cin % 64 == 32;  // remainder chunk of 32 channels: its own 32-channel / SWIZZLE_64B maps
+  tmap32 = tmap;
+  if (has_half)
+    if (int e = make_tmap(ctx, &tmap32, io.in, io.in_C, io.w, io.h, io.Nw, L.fp16, false, true)) return e;
+  tmap_v32 = tmap32;
   // Remainder strip (w not a multiple of 128): cover it with vertical runs when that wastes fewer MMA rows.
   const int wm = io.w / TC_RUN * TC_RUN, rem = io.w - wm;
   int max_grid = ctx->sm_count;
@@ -271,7 +282,8 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
     const int v_runs = (io.h + TC_RUN - 1) / TC_RUN, v_rows = (rem + R - 1) / R;
     const double eff_h = rem / (double)TC_RUN;
     const double eff_v = (io.h / (double)(v_runs * TC_RUN)) * (rem / (double)(v_rows * R));
-    if (eff_v > eff_h && max_grid >= 2 && make_tmap(ctx, &tmap_v, io.in, io.in_C, io.w, io.h, io.Nw, L.fp16, true) == 0) {
+    if (eff_v > eff_h && max_grid >= 2 && make_tmap(ctx, &tmap_v, io.in, io.in_C, io.w, io.h, io.Nw, L.fp16, true) == 0 &&
+        (!has_half || make_tmap(ctx, &tmap_v32, io.in, io.in_C, io.w, io.h, io.Nw, L.fp16, true, true) == 0)) {
       use_v = true;
       P.strip_x0 = wm;
       P.v_runs = v_runs;
@@ -306,9 +318,9 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
     WCUDA(ctx, cudaFuncSetAttribute(conv3x3_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
     ctx->tc_attr_set = true;
   }
-  if (N == 16) conv3x3_tc_kernel<16><<<grid, TC_THREADS, smem, st>>>(tmap, tmap_v, P);
-  else if (N == 32) conv3x3_tc_kernel<32><<<grid, TC_THREADS, smem, st>>>(tmap, tmap_v, P);
-  else conv3x3_tc_kernel<64><<<grid, TC_THREADS, smem, st>>>(tmap, tmap_v, P);
+  if (N == 16) conv3x3_tc_kernel<16><<<grid, TC_THREADS, smem, st>>>(tmap, tmap_v, tmap32, tmap_v32, P);
+  else if (N == 32) conv3x3_tc_kernel<32><<<grid, TC_THREADS, smem, st>>>(tmap, tmap_v, tmap32, tmap_v32, P);
+  else conv3x3_tc_kernel<64><<<grid, TC_THREADS, smem, st>>>(tmap, tmap_v, tmap32, tmap_v32, P);
   WLAUNCH_CHECK(ctx);
   return 0;
 }
@@ -370,7 +382,7 @@ int rrdbnet_batch(wowsr_ctx* ctx, ConvNet* net, const uint8_t* img, long long pi
     memset(&F, 0, sizeof F);
     F.img = img; F.pitch = pitch; F.cin = 3; F.win_xy = (const int*)net->winxy.p;
     F.Nw = nb; F.h = h; F.w = w; F.weight = net->first_w; F.bias = net->first_b;
-    F.f32_a = (float*)net->feat.p; F.f32_b = (float*)net->trunk.p; F.f32_c = (float*)net->rrdb.p;
+    F.f32_a = (float*)net->feat.p; F.f32_b = (float*)net->rrdb.p;  // rrdb = T0: the RRDB input x_rrdb
     F.f32 = fl;
     F.out_t = net->dense0.p; F.out_stride = 192; F.out_fp16 = body16; F.in_scale_div = 255.0f;
     dim3 grid((unsigned)((px + 127) / 128), 4);
@@ -393,11 +405,13 @@ int rrdbnet_batch(wowsr_ctx* ctx, ConvNet* net, const uint8_t* img, long long pi
       LayerIO io;
       io.in = cur; io.in_C = 192; io.Nw = nb; io.h = h; io.w = w;
       io.f32 = fl;
-      io.scale1 = 0.2f; io.res1 = (const float*)net->trunk.p;
-      io.out_f32_a = (float*)net->trunk.p;
+      // fp32 residual trunk without a separate copy of the RRDB input: T0 (`rrdb`) holds x_rrdb and stays
+      // untouched while rdb1/rdb2 run on T1 (`trunk`); rdb3 reads both and writes the next RRDB's input to T0.
+      io.scale1 = 0.2f;
+      io.res1 = (const float*)(r == 0 ? net->rrdb.p : net->trunk.p);
+      io.out_f32_a = (float*)(r == 2 ? net->rrdb.p : net->trunk.p);
       if (r == 2) {
         io.scale2 = 0.2f; io.res2 = (const float*)net->rrdb.p;
-        io.out_f32_b = (float*)net->rrdb.p;
       }
       io.out_t = nxt; io.out_stride = 192; io.out_choff = 0;
       // the last RDB feeds conv_body, which may run in a different operand type (mixed precision)

@@ -349,9 +349,10 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& P, bool vert,
 // NK consecutive K-steps (starting at KS0) of run-axis tap KX of one stage, as ONE asm block: the descriptor
 // bases reach the uniform datapath once and every MMA costs two 64-bit adds (immediates are compile-time:
 // A advances 32 B per K-step and 128 B per tap; B 32 B per K-step and 3*N rows per tap; units of 16 B).
-template <int N, int KX, int KS0, int NK>
+// SW = bytes per operand row: 128 (64-channel chunk, SWIZZLE_128B) or 64 (32-channel remainder chunk, SWIZZLE_64B).
+template <int N, int KX, int KS0, int NK, int SW = 128>
 __device__ __forceinline__ void mma_group(uint32_t col, uint64_t a, uint64_t b, uint32_t idesc) {
-  constexpr int A0 = KX * 8 + KS0 * 2, B0 = KX * 3 * N * 8 + KS0 * 2;
+  constexpr int A0 = KX * (SW / 16) + KS0 * 2, B0 = KX * 3 * N * (SW / 16) + KS0 * 2;
 #define WOWSR_MMA_STEP(IA, IB) \
   "add.u64 ta, %1, %" #IA ";\n\tadd.u64 tb, %2, %" #IB ";\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %3, p;\n\t"
 #define WOWSR_MMA_HEAD "{\n\t.reg .b64 ta, tb;\n\t.reg .pred p;\n\tsetp.eq.u32 p, 0, 0;\n\t"
@@ -377,31 +378,33 @@ __device__ __forceinline__ void mma_group(uint32_t col, uint64_t a, uint64_t b, 
 
 // First two run-axis taps of a stage.  `first_chunk`: the very first K-step of the tile must overwrite (not
 // accumulate into) the accumulator block of output row yy, which only the row-tap-0 (j = 2) block touches.
-template <int N, int NKS>
+template <int N, int NKS, int SW = 128>
 __device__ __forceinline__ void issue_taps01(bool first_chunk, uint32_t acc_base, int yy, int jlo, int jhi, uint32_t col,
                                              uint64_t a, uint64_t b, uint64_t bj, uint32_t idesc, uint32_t idesc_base) {
   if (first_chunk) {
     const uint32_t id1 = idesc_base | ((uint32_t)(N >> 3) << 17);
     if (jhi == 2) {
-      ptx::mma_f16_ss(acc_base + yy * N, a, b + (uint64_t)(2 * N * 8), id1, 0);
+      ptx::mma_f16_ss(acc_base + yy * N, a, b + (uint64_t)(2 * N * (SW / 16)), id1, 0);
       if (jlo <= 1) ptx::mma_f16_ss(col, a, bj, idesc_base | ((uint32_t)(((2 - jlo) * N) >> 3) << 17), 1);
     } else {
       ptx::mma_f16_ss(col, a, bj, idesc, 1);
     }
-    mma_group<N, 0, 1, NKS - 1>(col, a, bj, idesc);
+    mma_group<N, 0, 1, NKS - 1, SW>(col, a, bj, idesc);
   } else {
-    mma_group<N, 0, 0, NKS>(col, a, bj, idesc);
+    mma_group<N, 0, 0, NKS, SW>(col, a, bj, idesc);
   }
-  mma_group<N, 1, 0, NKS>(col, a, bj, idesc);
+  mma_group<N, 1, 0, NKS, SW>(col, a, bj, idesc);
 }
 
 template <int N>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__ CUtensorMap tmap_v, const ConvParams P) {
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__ CUtensorMap tmap_v,
+                  const __grid_constant__ CUtensorMap tmap_h32, const __grid_constant__ CUtensorMap tmap_v32, const ConvParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool vert = (int)blockIdx.x >= P.grid_h;
   const CUtensorMap& tmap = vert ? tmap_v : tmap_h;
+  const CUtensorMap& tmap32 = vert ? tmap_v32 : tmap_h32;  // 32-channel box, SWIZZLE_64B: the remainder chunk when Cin % 64 == 32
   const uint8_t* wpack = vert ? P.wpack_v : P.wpack;
   const int tile0 = vert ? (int)blockIdx.x - P.grid_h : (int)blockIdx.x;
   const int tile_step = vert ? (int)gridDim.x - P.grid_h : P.grid_h;
@@ -463,9 +466,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
             if (P.flags & CF_DBG_NO_TMA) {
               ptx::mbar_arrive(ptx::smem_u32(&ctl->w_full[b]));
             } else {
-              ptx::mbar_arrive_expect_tx(ptx::smem_u32(&ctl->w_full[b]), P.w_chunk_bytes);
-              ptx::bulk_load(w_smem + b * P.w_chunk_bytes, wpack + (size_t)c * P.w_chunk_bytes, P.w_chunk_bytes,
-                             ptx::smem_u32(&ctl->w_full[b]));
+              const uint32_t wbytes = (P.cin - c * 64) < 64 ? P.w_chunk_bytes / 2 : P.w_chunk_bytes;
+              ptx::mbar_arrive_expect_tx(ptx::smem_u32(&ctl->w_full[b]), wbytes);
+              ptx::bulk_load(w_smem + b * P.w_chunk_bytes, wpack + (size_t)c * P.w_chunk_bytes, wbytes, ptx::smem_u32(&ctl->w_full[b]));
             }
           }
           wcount++;
@@ -476,9 +479,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
             if (P.flags & CF_DBG_NO_TMA) {
               ptx::mbar_arrive(ptx::smem_u32(&ctl->a_full[stage]));
             } else {
-              ptx::mbar_arrive_expect_tx(ptx::smem_u32(&ctl->a_full[stage]), 2 * TC_ABYTES);
-              ptx::tma_load_4d(a_smem + stage * TC_ASTAGE, &tmap, ptx::smem_u32(&ctl->a_full[stage]), c * 64, tc.u0 - 1,
-                               tc.v0 - 1 + 2 * sp, tc.n);
+              const bool half_c = (P.cin - c * 64) < 64;
+              ptx::mbar_arrive_expect_tx(ptx::smem_u32(&ctl->a_full[stage]), half_c ? TC_ABYTES : 2 * TC_ABYTES);
+              ptx::tma_load_4d(a_smem + stage * TC_ASTAGE, half_c ? &tmap32 : &tmap, ptx::smem_u32(&ctl->a_full[stage]), c * 64,
+                               tc.u0 - 1, tc.v0 - 1 + 2 * sp, tc.n);
             }
           }
           if (++stage == P.n_stage) { stage = 0; aphase ^= 1; }
@@ -493,8 +497,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
     // last tap group of the current one so its latency hides behind queued tensor work.
     const bool leader = ptx::elect_one() && !(P.flags & CF_DBG_NO_MMA);
     const bool committer = ptx::elect_one();
-    const uint64_t adesc0 = ptx::smem_desc_sw128(a_smem, 1024, 0);
-    const uint64_t bdesc0 = ptx::smem_desc_sw128(w_smem, 1024, 0);
+    const uint64_t adesc128 = ptx::smem_desc_sw128(a_smem, 1024, 0), bdesc128 = ptx::smem_desc_sw128(w_smem, 1024, 0);
+    const uint64_t adesc64 = ptx::smem_desc_sw64(a_smem, 512), bdesc64 = ptx::smem_desc_sw64(w_smem, 512);
     const uint32_t full0 = ptx::smem_u32(&ctl->a_full[0]), empty0 = ptx::smem_u32(&ctl->a_empty[0]);
     const int n_my = tile0 < tile_end ? (tile_end - tile0 + tile_step - 1) / tile_step : 0;
     const uint32_t idesc_base = P.idesc_base;
@@ -519,7 +523,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
           wb = c;
         }
         ptx::tc_fence_after();
-        const uint64_t bd = bdesc0 + (uint64_t)((wb * P.w_chunk_bytes) >> 4);
+        const uint64_t adesc0 = half_chunk ? adesc64 : adesc128;
+        const uint64_t bd = (half_chunk ? bdesc64 : bdesc128) + (uint64_t)((wb * P.w_chunk_bytes) >> 4);
         const bool first_chunk = c == 0;
 #pragma unroll
         for (int sp = 0; sp < (R + 2) / 2; sp++) {
@@ -535,19 +540,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
             const int jhi = R + 1 - yy < 2 ? R + 1 - yy : 2;
             const uint32_t idesc = idesc_base | ((uint32_t)(((jhi - jlo + 1) * N) >> 3) << 17);
             const uint32_t col = acc_base + (yy - 2 + jlo) * N;
-            const uint64_t ad = ad0 + (uint64_t)(half * (TC_ABYTES >> 4));
-            const uint64_t bj = bd + (uint64_t)(jlo * N * 8);
+            // second row of the stage: 130 pixels further; operand rows are 128 B (full chunk) or 64 B (32-ch chunk)
+            const uint64_t ad = ad0 + (uint64_t)(half * (half_chunk ? (TC_ABYTES >> 5) : (TC_ABYTES >> 4)));
+            const uint64_t bj = bd + (uint64_t)(jlo * N * (half_chunk ? 4 : 8));
             if (leader) {
-              if (half_chunk) issue_taps01<N, 2>(first_chunk, acc_base, yy, jlo, jhi, col, ad, bd, bj, idesc, idesc_base);
-              else issue_taps01<N, 4>(first_chunk, acc_base, yy, jlo, jhi, col, ad, bd, bj, idesc, idesc_base);
+              if (half_chunk) issue_taps01<N, 2, 64>(first_chunk, acc_base, yy, jlo, jhi, col, ad, bd, bj, idesc, idesc_base);
+              else issue_taps01<N, 4, 128>(first_chunk, acc_base, yy, jlo, jhi, col, ad, bd, bj, idesc, idesc_base);
             }
             if (half == 1 && !last) {  // prefetch-wait for the next stage, hidden behind the MMAs queued above
               if (!ptx::mbar_wait_wd(full0 + 8 * ns, np, wd)) tc_fail(P, 23);
               ptx::tc_fence_after();
             }
             if (leader) {
-              if (half_chunk) mma_group<N, 2, 0, 2>(col, ad, bj, idesc);
-              else mma_group<N, 2, 0, 4>(col, ad, bj, idesc);
+              if (half_chunk) mma_group<N, 2, 0, 2, 64>(col, ad, bj, idesc);
+              else mma_group<N, 2, 0, 4, 128>(col, ad, bj, idesc);
             }
           }
           if (committer) ptx::mma_commit(empty0 + 8 * stage);

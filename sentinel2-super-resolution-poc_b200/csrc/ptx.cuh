@@ -150,6 +150,17 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr, uint32_t sbo_
   return d;
 }
 
+// Same for 64-byte rows (32 x 16-bit) with the 64-byte swizzle: layout type 4, 8-row groups 512 B apart.
+__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+
 }  // namespace ptx
 
 // Instruction descriptor for kind::f16: [4,6) D format (1 = f32) | [7,10) A format | [10,13) B format
