@@ -171,7 +171,7 @@ int make_tmap(wowsr_ctx* ctx, CUtensorMap* m, const void* base, int C, int W, in
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base),
                    dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, half ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   half ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return wowsr_fail(ctx, WOWSR_ERR_CUDA, "cuTensorMapEncodeTiled(C=%d,W=%d,H=%d,N=%d) -> CUresult %d", C, W, H, Nw, (int)r);
   return 0;
