@@ -9,7 +9,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwowsr.so")
+LIB_PATH = os.environ.get("WOWSR_LIB", os.path.join(_HERE, "libwowsr.so"))  # override only for A/B kernel experiments
 
 PREC = {"bf16_pure": 0, "fp16": 1, "bf16": 2, "mixed": 2}
 

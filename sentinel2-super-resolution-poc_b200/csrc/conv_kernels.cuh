@@ -50,8 +50,8 @@ struct WinDev {  // output-resolution window record for the final layer
 
 // Warp-blocked layout of the fp32 trunk buffers (feat / trunk / rrdb_in).  The 32 lanes of an epilogue warp
 // own 32 consecutive pixels along the tile's run axis and each lane touches all channels of its pixel, so
-// the buffers are stored [..][32-pixel block][channel][pixel in block]: every per-channel access of a warp is
-// ONE coalesced 128-byte wavefront (the plain [pixel][64 ch] layout costs 32 wavefronts per access).
+// the buffers are stored [..][32-pixel block][channel/4][pixel in block][channel%4]: a warp access is 512
+// contiguous bytes (the plain [pixel][64 ch] layout costs 32 wavefronts per 16-byte-per-lane access).
 // Pixels x < x0 are blocked along x (horizontal tiles); the remainder strip x >= x0 is blocked along y
 // (vertical tiles) and stored after the main region.
 struct F32Layout {
@@ -61,9 +61,11 @@ struct F32Layout {
   int rem;              // strip width
   long long strip_off;  // element offset of the strip region
 };
+// Element index of channel `ch` (multiple of 4) of pixel (n, y, x): a 32-pixel block stores [ch/4][pixel][ch%4], so a
+// lane reads/writes 4 channels as one float4 and the 32 lanes of a warp cover 512 contiguous bytes per access.
 __device__ __forceinline__ long long f32_index(const F32Layout& L, int h, int n, int y, int x, int ch) {
-  if (x < L.x0) return ((((long long)n * h + y) * L.wpb + (x >> 5)) * 64 + ch) * 32 + (x & 31);
-  return L.strip_off + ((((long long)n * L.rem + (x - L.x0)) * L.hpb + (y >> 5)) * 64 + ch) * 32 + (y & 31);
+  if (x < L.x0) return ((((long long)n * h + y) * L.wpb + (x >> 5)) * 64 + ch) * 32 + (x & 31) * 4;
+  return L.strip_off + ((((long long)n * L.rem + (x - L.x0)) * L.hpb + (y >> 5)) * 64 + ch) * 32 + (y & 31) * 4;
 }
 
 struct ConvParams {
@@ -155,20 +157,30 @@ __device__ __forceinline__ void epilogue_pixel(const ConvParams& P, int n, int y
   if (P.f32.wpb) {
     const long long fb = valid ? f32_index(P.f32, P.h, n, y, x, ch0) : 0;
     if (P.res1) {
-      const float* r = P.res1 + fb;
-      float t[NCH];
+      const float4* r = reinterpret_cast<const float4*>(P.res1 + fb);
+      float4 t[NCH / 4];
 #pragma unroll
-      for (int i = 0; i < NCH; i++) t[i] = valid ? r[i * 32] : 0.0f;
+      for (int i = 0; i < NCH / 4; i++) t[i] = valid ? r[i * 32] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < NCH; i++) v[i] = __fadd_rn(__fmul_rn(v[i], P.scale1), t[i]);
+      for (int i = 0; i < NCH / 4; i++) {
+        v[4 * i + 0] = __fadd_rn(__fmul_rn(v[4 * i + 0], P.scale1), t[i].x);
+        v[4 * i + 1] = __fadd_rn(__fmul_rn(v[4 * i + 1], P.scale1), t[i].y);
+        v[4 * i + 2] = __fadd_rn(__fmul_rn(v[4 * i + 2], P.scale1), t[i].z);
+        v[4 * i + 3] = __fadd_rn(__fmul_rn(v[4 * i + 3], P.scale1), t[i].w);
+      }
     }
     if (P.res2) {
-      const float* r = P.res2 + fb;
-      float t[NCH];
+      const float4* r = reinterpret_cast<const float4*>(P.res2 + fb);
+      float4 t[NCH / 4];
 #pragma unroll
-      for (int i = 0; i < NCH; i++) t[i] = valid ? r[i * 32] : 0.0f;
+      for (int i = 0; i < NCH / 4; i++) t[i] = valid ? r[i * 32] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < NCH; i++) v[i] = __fadd_rn(__fmul_rn(v[i], P.scale2), t[i]);
+      for (int i = 0; i < NCH / 4; i++) {
+        v[4 * i + 0] = __fadd_rn(__fmul_rn(v[4 * i + 0], P.scale2), t[i].x);
+        v[4 * i + 1] = __fadd_rn(__fmul_rn(v[4 * i + 1], P.scale2), t[i].y);
+        v[4 * i + 2] = __fadd_rn(__fmul_rn(v[4 * i + 2], P.scale2), t[i].z);
+        v[4 * i + 3] = __fadd_rn(__fmul_rn(v[4 * i + 3], P.scale2), t[i].w);
+      }
     }
     if (P.act) {
       const float slope = P.act == 1 ? 0.2f : 0.0f;
@@ -176,14 +188,14 @@ __device__ __forceinline__ void epilogue_pixel(const ConvParams& P, int n, int y
       for (int i = 0; i < NCH; i++) v[i] = fmaxf(v[i], __fmul_rn(v[i], slope));
     }
     if (P.out_f32_a && valid) {
-      float* o = P.out_f32_a + fb;
+      float4* o = reinterpret_cast<float4*>(P.out_f32_a + fb);
 #pragma unroll
-      for (int i = 0; i < NCH; i++) o[i * 32] = v[i];
+      for (int i = 0; i < NCH / 4; i++) o[i * 32] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
     }
     if (P.out_f32_b && valid) {
-      float* o = P.out_f32_b + fb;
+      float4* o = reinterpret_cast<float4*>(P.out_f32_b + fb);
 #pragma unroll
-      for (int i = 0; i < NCH; i++) o[i * 32] = v[i];
+      for (int i = 0; i < NCH / 4; i++) o[i * 32] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
     }
   } else if (valid) {
     if (P.res1) {
@@ -450,7 +462,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
   // A pipeline stage holds TWO consecutive input rows (one TMA box of 2 x 130 pixels x 64 channels): the
   // tensor pipe accepts only ~2 queued MMAs, so every scalar instruction between MMAs is a bubble and the
   // per-stage handshake (mbarrier wait, commit, loop) must be amortised over as many MMAs as possible.
-  uint32_t wd = 1u << 26;  // watchdog poll budget; collapses after the first timeout so a bug cannot hang the GPU
+  uint32_t wd = 1u << 18;  // watchdog poll budget (each poll may park up to 100 us); collapses after the first timeout
   if (warp == TC_WARP_TMA) {
     // ===================== TMA producer =====================
     const bool leader = ptx::elect_one();
@@ -742,9 +754,9 @@ conv_first_kernel(const FirstParams P) {
   for (int k = 0; k < 3; k++)
     if (outs[k]) {
       if (P.f32.wpb) {
-        float* o = outs[k] + f32_index(P.f32, P.h, n, y, x, qd * 16);
+        float4* o = reinterpret_cast<float4*>(outs[k] + f32_index(P.f32, P.h, n, y, x, qd * 16));
 #pragma unroll
-        for (int i = 0; i < 16; i++) o[i * 32] = acc[i];
+        for (int i = 0; i < 4; i++) o[i * 32] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
       } else {
         float4* o = reinterpret_cast<float4*>(outs[k] + pix * 64 + qd * 16);
 #pragma unroll

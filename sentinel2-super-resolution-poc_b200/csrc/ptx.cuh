@@ -35,13 +35,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       // the suspend-time hint lets the hardware park the polling warp instead of re-issuing the probe
       "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
       : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(0x989680u)
+      : "r"(bar), "r"(parity), "r"(100000u)  /* suspend-time hint, ns */
       : "memory");
   return ok != 0;
 }
 // Bounded wait: returns false if the barrier did not flip within ~`limit` polls (watchdog so a
 // protocol bug turns into an error code instead of a hung GPU).
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, uint32_t limit = 1u << 26) {
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, uint32_t limit = 1u << 18) {
 #pragma unroll 1
   for (uint32_t i = 0; i < limit; i++)
     if (mbar_try_wait(bar, parity)) return true;
