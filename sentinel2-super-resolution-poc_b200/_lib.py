@@ -135,8 +135,8 @@ class Handle:
         return dict(zip(("total", "head", "trunk", "tail"), list(buf)[:n]))
 
     def debug_trace(self):
-        buf = (C.c_int64 * 256)()
-        n = self._L.wowsr_debug_trace(self._h, buf, 256)
+        buf = (C.c_int64 * 512)()  # rows 0..63: tile timeline; rows 64..127: epilogue breakdown (instrumented builds)
+        n = self._L.wowsr_debug_trace(self._h, buf, 512)
         return np.array(list(buf)[:max(n, 0)], dtype=np.int64).reshape(-1, 4)
 
     # -- post-process -------------------------------------------------------------------------

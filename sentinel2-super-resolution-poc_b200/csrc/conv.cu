@@ -248,8 +248,8 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
   {  // debug tracing of one launch: option tc_trace_layer = 1-based index of the conv launch to trace
     int64_t tl = wowsr_opt(ctx, "tc_trace_layer", 0);
     if (tl > 0 && ++ctx->trace_counter == tl) {
-      if (int e = wowsr_ensure(ctx, ctx->trace_buf, 64 * 4 * 8)) return e;
-      cudaMemsetAsync(ctx->trace_buf.p, 0, 64 * 4 * 8, st);
+      if (int e = wowsr_ensure(ctx, ctx->trace_buf, 2 * 64 * 4 * 8)) return e;
+      cudaMemsetAsync(ctx->trace_buf.p, 0, 2 * 64 * 4 * 8, st);
       P.trace = (long long*)ctx->trace_buf.p;
     }
   }
@@ -312,15 +312,29 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
     }
   }
   size_t smem = (size_t)P.n_stage * TC_ASTAGE + (size_t)P.n_wbuf * L.chunk_bytes + SMEM_SLACK;
+  // epilogue specialisation (conv_kernels.cuh): the generic path handles every other layer shape
+  int mode = EPI_GENERIC;
+  if (!wowsr_opt(ctx, "tc_generic_epilogue", 0) && N >= 32 && !P.final && P.out_t && P.out_rep == 1 && !P.out_ps && !P.out_f32_b &&
+      !(P.flags & CF_DBG_NO_STORE)) {
+    if (!P.res1 && !P.res2 && !P.out_f32_a) mode = EPI_PLAIN;
+    else if (N == 64 && P.f32.wpb && P.res1 && P.out_f32_a) mode = EPI_RES;
+  }
   if (!ctx->tc_attr_set) {  // per device (one handle per device)
-    WCUDA(ctx, cudaFuncSetAttribute(conv3x3_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
-    WCUDA(ctx, cudaFuncSetAttribute(conv3x3_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
-    WCUDA(ctx, cudaFuncSetAttribute(conv3x3_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+    WCUDA(ctx, cudaFuncSetAttribute(conv3x3_tc_kernel<16, EPI_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+    WCUDA(ctx, cudaFuncSetAttribute(conv3x3_tc_kernel<32, EPI_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+    WCUDA(ctx, cudaFuncSetAttribute(conv3x3_tc_kernel<64, EPI_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+    WCUDA(ctx, cudaFuncSetAttribute(conv3x3_tc_kernel<32, EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+    WCUDA(ctx, cudaFuncSetAttribute(conv3x3_tc_kernel<64, EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+    WCUDA(ctx, cudaFuncSetAttribute(conv3x3_tc_kernel<64, EPI_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
     ctx->tc_attr_set = true;
   }
-  if (N == 16) conv3x3_tc_kernel<16><<<grid, TC_THREADS, smem, st>>>(tmap, tmap_v, tmap32, tmap_v32, P);
-  else if (N == 32) conv3x3_tc_kernel<32><<<grid, TC_THREADS, smem, st>>>(tmap, tmap_v, tmap32, tmap_v32, P);
-  else conv3x3_tc_kernel<64><<<grid, TC_THREADS, smem, st>>>(tmap, tmap_v, tmap32, tmap_v32, P);
+#define TC_LAUNCH(NN, MM) conv3x3_tc_kernel<NN, MM><<<grid, TC_THREADS, smem, st>>>(tmap, tmap_v, tmap32, tmap_v32, P)
+  if (N == 16) TC_LAUNCH(16, EPI_GENERIC);
+  else if (N == 32) { if (mode == EPI_PLAIN) TC_LAUNCH(32, EPI_PLAIN); else TC_LAUNCH(32, EPI_GENERIC); }
+  else if (mode == EPI_PLAIN) TC_LAUNCH(64, EPI_PLAIN);
+  else if (mode == EPI_RES) TC_LAUNCH(64, EPI_RES);
+  else TC_LAUNCH(64, EPI_GENERIC);
+#undef TC_LAUNCH
   WLAUNCH_CHECK(ctx);
   return 0;
 }
@@ -573,7 +587,7 @@ extern "C" int wowsr_enhance_host(wowsr_ctx* ctx, const uint8_t* img_host, int32
 extern "C" int32_t wowsr_debug_trace(wowsr_ctx* ctx, int64_t* out, int32_t cap) {
   if (!ctx || !out || !ctx->trace_buf.p) return WOWSR_ERR_ARG;
   DeviceGuard g(ctx->device);
-  int n = cap < 256 ? cap : 256;
+  int n = cap < 512 ? cap : 512;
   if (cudaMemcpy(out, ctx->trace_buf.p, (size_t)n * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return WOWSR_ERR_CUDA;
   ctx->trace_counter = 0;
   return n;

@@ -24,7 +24,10 @@
 
 #include "ptx.cuh"
 
-constexpr int TC_EPI_WARPS = 8;       // epilogue warps: warp w drains TMEM lane quarter w%4, tile rows r with r%2 == w/4
+#ifndef WOWSR_EPI_WARPS
+#define WOWSR_EPI_WARPS 8
+#endif
+constexpr int TC_EPI_WARPS = WOWSR_EPI_WARPS;  // epilogue warps: warp w drains TMEM lane quarter w%4, tile rows r = w/4 (mod EPI_WARPS/4)
 constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;  // + TMA producer warp + MMA issuer warp
 // The issuing warps get the HIGHEST warp ids: the sub-partition arbiter favours higher ids, and an MMA issuer
 // that shares a sub-partition with a busy epilogue warp of higher id gets starved (measured).
@@ -320,6 +323,150 @@ __device__ __forceinline__ void epilogue_pixel(const ConvParams& P, int n, int y
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// specialised epilogues of the tensor-core kernel (the two layer shapes that make up 97 % of a forward)
+//   EPI_PLAIN: bias (+ LeakyReLU / ReLU) -> 16-bit channel-offset store            (rdb.conv1-4, conv_up2, conv_hr)
+//   EPI_RES:   bias, v*s1 + res1 [, v*s2 + res2] in fp32 (warp-blocked buffers), fp32 trunk store, 16-bit store (rdb.conv5)
+// Everything that is constant for the launch is read from the parameter block ONCE (EpiConst) instead of once per
+// 32-channel iteration: with only two to four epilogue warps per scheduler the chain of constant loads and
+// uniform branches of the generic path was most of an iteration's latency (profiles/r01_epilogue_breakdown.txt).
+// ---------------------------------------------------------------------------------------------
+enum { EPI_GENERIC = 0, EPI_PLAIN = 1, EPI_RES = 2 };
+
+struct EpiConst {
+  bool do_act, out_fp16, has_res2;
+  float slope, scale1, scale2;
+  uint16_t* out_t;        // + channel offset
+  long long out_stride;   // elements per pixel
+  const float* res1;
+  const float* res2;
+  float* out_f32;
+};
+
+__device__ __forceinline__ EpiConst make_epi_const(const ConvParams& P) {
+  EpiConst E;
+  E.do_act = P.act != 0;
+  E.slope = P.act == 1 ? 0.2f : 0.0f;
+  E.out_fp16 = (P.flags & CF_OUT_FP16) != 0;
+  E.has_res2 = P.res2 != nullptr;
+  E.scale1 = P.scale1;
+  E.scale2 = P.scale2;
+  E.out_t = reinterpret_cast<uint16_t*>(P.out_t) + P.out_choff;
+  E.out_stride = P.out_stride;
+  E.res1 = P.res1;
+  E.res2 = P.res2;
+  E.out_f32 = P.out_f32_a;
+  return E;
+}
+
+__device__ __forceinline__ void epi_bias32(float (&v)[32], const float* __restrict__ bias) {
+  const float4* b4 = reinterpret_cast<const float4*>(bias);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const float4 b = b4[i];
+    v[4 * i + 0] = __fadd_rn(v[4 * i + 0], b.x);
+    v[4 * i + 1] = __fadd_rn(v[4 * i + 1], b.y);
+    v[4 * i + 2] = __fadd_rn(v[4 * i + 2], b.z);
+    v[4 * i + 3] = __fadd_rn(v[4 * i + 3], b.w);
+  }
+}
+
+// pack 32 fp32 values to 16-bit, transpose the 16-byte pieces inside lane quads and store: slot k of lane 4i+j ends
+// up holding piece j of pixel 4i+k, so each store instruction writes 64 contiguous bytes per quad.
+// `px` = address of channel ch0 of this lane's pixel; `step` = elements between consecutive pixels of the run.
+__device__ __forceinline__ void epi_store16_quad(const float (&v)[32], bool fp16, uint16_t* px, long long step, int u, int u_lim) {
+  uint32_t pk[16];
+  if (fp16) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+      pk[i] = *reinterpret_cast<uint32_t*>(&hh);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      __nv_bfloat162 bb = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      pk[i] = *reinterpret_cast<uint32_t*>(&bb);
+    }
+  }
+  const int j = threadIdx.x & 3;
+#pragma unroll
+  for (int m = 1; m <= 2; m <<= 1) {
+    const bool up = (j & m) != 0;
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      if (a & m) continue;
+      const int b2 = a | m;
+#pragma unroll
+      for (int q4 = 0; q4 < 4; q4++) {
+        const uint32_t send = up ? pk[4 * a + q4] : pk[4 * b2 + q4];
+        const uint32_t recv = __shfl_xor_sync(0xFFFFFFFFu, send, m);
+        if (up) pk[4 * a + q4] = recv;
+        else pk[4 * b2 + q4] = recv;
+      }
+    }
+  }
+  uint16_t* base = px + j * 8;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int d = k - j;  // pixel offset along the run axis
+    if (u + d < u_lim && u + d >= 0)
+      *reinterpret_cast<uint4*>(base + (long long)d * step) = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+  }
+}
+
+__device__ __forceinline__ void epi_plain32(const EpiConst& E, float (&v)[32], const float* __restrict__ bias, uint16_t* px,
+                                            long long step, int u, int u_lim) {
+  epi_bias32(v, bias);
+  if (E.do_act) {
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i], __fmul_rn(v[i], E.slope));
+  }
+  epi_store16_quad(v, E.out_fp16, px, step, u, u_lim);
+}
+
+// `fb` = element index of channel ch0 of this lane's pixel in the warp-blocked fp32 buffers (f32_index)
+__device__ __forceinline__ void epi_res32(const EpiConst& E, float (&v)[32], const float* __restrict__ bias, long long fb, bool valid,
+                                          uint16_t* px, long long step, int u, int u_lim) {
+  float4 t[8];
+  {
+    const float4* r = reinterpret_cast<const float4*>(E.res1 + fb);
+#pragma unroll
+    for (int i = 0; i < 8; i++) t[i] = valid ? r[i * 32] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  epi_bias32(v, bias);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    v[4 * i + 0] = __fadd_rn(__fmul_rn(v[4 * i + 0], E.scale1), t[i].x);
+    v[4 * i + 1] = __fadd_rn(__fmul_rn(v[4 * i + 1], E.scale1), t[i].y);
+    v[4 * i + 2] = __fadd_rn(__fmul_rn(v[4 * i + 2], E.scale1), t[i].z);
+    v[4 * i + 3] = __fadd_rn(__fmul_rn(v[4 * i + 3], E.scale1), t[i].w);
+  }
+  if (E.has_res2) {
+    const float4* r = reinterpret_cast<const float4*>(E.res2 + fb);
+#pragma unroll
+    for (int i = 0; i < 8; i++) t[i] = valid ? r[i * 32] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      v[4 * i + 0] = __fadd_rn(__fmul_rn(v[4 * i + 0], E.scale2), t[i].x);
+      v[4 * i + 1] = __fadd_rn(__fmul_rn(v[4 * i + 1], E.scale2), t[i].y);
+      v[4 * i + 2] = __fadd_rn(__fmul_rn(v[4 * i + 2], E.scale2), t[i].z);
+      v[4 * i + 3] = __fadd_rn(__fmul_rn(v[4 * i + 3], E.scale2), t[i].w);
+    }
+  }
+  if (E.do_act) {
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i], __fmul_rn(v[i], E.slope));
+  }
+  if (valid) {
+    float4* o = reinterpret_cast<float4*>(E.out_f32 + fb);
+#pragma unroll
+    for (int i = 0; i < 8; i++) o[i * 32] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  }
+  epi_store16_quad(v, E.out_fp16, px, step, u, u_lim);
+}
+
 // ---------------------------------------------------------------------------------------------
 // tensor-core kernel
 // ---------------------------------------------------------------------------------------------
@@ -390,10 +537,10 @@ __device__ __forceinline__ void mma_group(uint32_t col, uint64_t a, uint64_t b, 
 
 // First two run-axis taps of a stage.  `first_chunk`: the very first K-step of the tile must overwrite (not
 // accumulate into) the accumulator block of output row yy, which only the row-tap-0 (j = 2) block touches.
-template <int N, int NKS, int SW = 128>
-__device__ __forceinline__ void issue_taps01(bool first_chunk, uint32_t acc_base, int yy, int jlo, int jhi, uint32_t col,
+template <int N, int NKS, int SW, bool FIRST>
+__device__ __forceinline__ void issue_taps01(uint32_t acc_base, int yy, int jlo, int jhi, uint32_t col,
                                              uint64_t a, uint64_t b, uint64_t bj, uint32_t idesc, uint32_t idesc_base) {
-  if (first_chunk) {
+  if constexpr (FIRST) {
     const uint32_t id1 = idesc_base | ((uint32_t)(N >> 3) << 17);
     if (jhi == 2) {
       ptx::mma_f16_ss(acc_base + yy * N, a, b + (uint64_t)(2 * N * (SW / 16)), id1, 0);
@@ -408,7 +555,101 @@ __device__ __forceinline__ void issue_taps01(bool first_chunk, uint32_t acc_base
   mma_group<N, 1, 0, NKS, SW>(col, a, bj, idesc);
 }
 
-template <int N>
+// Issue state of the MMA warp that survives across chunks and tiles.
+struct IssueState {
+  int stage;
+  uint32_t aphase;
+  uint32_t wd;
+};
+
+// All MMAs of ONE 64-channel (HALF: 32-channel) chunk of a tile: (R+2)/2 two-row stages, each 2 x 3 run-axis taps x
+// NKS K-steps.  FIRST (first chunk of the tile: overwrite instead of accumulate) and HALF are compile-time so the
+// unrolled issue path carries no per-row branches.  SINGLE: the caller runs this on one elected lane only (no
+// warp-level reconvergence points between MMAs); otherwise the whole warp runs it and `leader` gates the issue.
+template <int N, int R, bool FIRST, bool HALF, bool SINGLE>
+__device__ __forceinline__ void issue_chunk(const ConvParams& P, IssueState& S, bool leader, bool committer, bool last_chunk,
+                                            uint32_t full0, uint32_t empty0, uint64_t adesc0, uint64_t bd, uint32_t acc_base,
+                                            uint32_t idesc_base) {
+  constexpr int NKS = HALF ? 2 : 4, SW = HALF ? 64 : 128;
+#pragma unroll
+  for (int sp = 0; sp < (R + 2) / 2; sp++) {
+    const bool last = (sp == (R + 2) / 2 - 1) && last_chunk;
+    const uint64_t ad0 = adesc0 + (uint64_t)(S.stage * (TC_ASTAGE >> 4));
+    int ns = S.stage + 1;
+    uint32_t np = S.aphase;
+    if (ns == P.n_stage) { ns = 0; np ^= 1; }
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      const int yy = 2 * sp + half;  // compile-time after unrolling
+      const int jlo = yy < 2 ? 2 - yy : 0;
+      const int jhi = R + 1 - yy < 2 ? R + 1 - yy : 2;
+      const uint32_t idesc = idesc_base | ((uint32_t)(((jhi - jlo + 1) * N) >> 3) << 17);
+      const uint32_t col = acc_base + (yy - 2 + jlo) * N;
+      // second row of the stage: 130 pixels further; operand rows are 128 B (full chunk) or 64 B (32-ch chunk)
+      const uint64_t ad = ad0 + (uint64_t)(half * (HALF ? (TC_ABYTES >> 5) : (TC_ABYTES >> 4)));
+      const uint64_t bj = bd + (uint64_t)(jlo * N * (HALF ? 4 : 8));
+      if (leader) issue_taps01<N, NKS, SW, FIRST>(acc_base, yy, jlo, jhi, col, ad, bd, bj, idesc, idesc_base);
+      if (half == 1 && !last) {  // prefetch-wait for the next stage, hidden behind the MMAs queued above
+        if (!ptx::mbar_wait_hot(full0 + 8 * ns, np, S.wd)) tc_fail(P, 23);
+        ptx::tc_fence_after();
+      }
+      if (leader) mma_group<N, 2, 0, NKS, SW>(col, ad, bj, idesc);
+    }
+    if (committer) ptx::mma_commit(empty0 + 8 * S.stage);
+    if constexpr (!SINGLE) __syncwarp();
+    S.stage = ns;
+    S.aphase = np;
+  }
+}
+
+// The MMA issuer role for all tiles of this CTA.
+template <int N, int R, bool SINGLE>
+__device__ __forceinline__ void mma_issuer(const ConvParams& P, TcSmemCtl* ctl, bool leader, bool committer, uint32_t a_smem,
+                                           uint32_t w_smem, uint32_t tmem_base, int n_my) {
+  const uint64_t adesc128 = ptx::smem_desc_sw128(a_smem, 1024, 0), bdesc128 = ptx::smem_desc_sw128(w_smem, 1024, 0);
+  const uint64_t adesc64 = ptx::smem_desc_sw64(a_smem, 512), bdesc64 = ptx::smem_desc_sw64(w_smem, 512);
+  const uint32_t full0 = ptx::smem_u32(&ctl->a_full[0]), empty0 = ptx::smem_u32(&ctl->a_empty[0]);
+  const uint32_t idesc_base = P.idesc_base;
+  IssueState S{0, 0u, 1u << 18};  // watchdog poll budget; collapses after the first timeout
+  uint32_t wcount = 0;
+  if (n_my > 0 && !ptx::mbar_wait_hot(full0, 0, S.wd)) tc_fail(P, 23);
+  for (int it = 0; it < n_my; it++) {
+    const int accbuf = it & 1;
+    const uint32_t acc_phase = (it >> 1) & 1;
+    if (!ptx::mbar_wait_hot(ptx::smem_u32(&ctl->t_empty[accbuf]), acc_phase ^ 1, S.wd)) tc_fail(P, 21);
+    if (P.trace && blockIdx.x == 0 && committer && it < 64) P.trace[it * 4 + 0] = clock64();
+    ptx::tc_fence_after();
+    const uint32_t acc_base = tmem_base + accbuf * R * N;
+    for (int c = 0; c < P.n_chunks; c++) {
+      const bool half_chunk = (P.cin - c * 64) < 64;  // 32 valid channels: 2 K-steps instead of 4
+      uint32_t wb;
+      if (!(P.w_resident && it > 0)) {
+        wb = wcount % P.n_wbuf;
+        if (!ptx::mbar_wait_hot(ptx::smem_u32(&ctl->w_full[wb]), (wcount / P.n_wbuf) & 1, S.wd)) tc_fail(P, 22);
+        wcount++;
+      } else {
+        wb = c;
+      }
+      ptx::tc_fence_after();
+      const uint64_t adesc0 = half_chunk ? adesc64 : adesc128;
+      const uint64_t bd = (half_chunk ? bdesc64 : bdesc128) + (uint64_t)((wb * P.w_chunk_bytes) >> 4);
+      const bool last_chunk = (c == P.n_chunks - 1) && (it == n_my - 1);
+      if (c == 0) {
+        if (half_chunk) issue_chunk<N, R, true, true, SINGLE>(P, S, leader, committer, last_chunk, full0, empty0, adesc0, bd, acc_base, idesc_base);
+        else issue_chunk<N, R, true, false, SINGLE>(P, S, leader, committer, last_chunk, full0, empty0, adesc0, bd, acc_base, idesc_base);
+      } else {
+        if (half_chunk) issue_chunk<N, R, false, true, SINGLE>(P, S, leader, committer, last_chunk, full0, empty0, adesc0, bd, acc_base, idesc_base);
+        else issue_chunk<N, R, false, false, SINGLE>(P, S, leader, committer, last_chunk, full0, empty0, adesc0, bd, acc_base, idesc_base);
+      }
+      if (!P.w_resident && committer) ptx::mma_commit(ptx::smem_u32(&ctl->w_empty[wb]));
+    }
+    if (committer) ptx::mma_commit(ptx::smem_u32(&ctl->t_full[accbuf]));
+    if (P.trace && blockIdx.x == 0 && committer && it < 64) P.trace[it * 4 + 1] = clock64();
+    if constexpr (!SINGLE) __syncwarp();
+  }
+}
+
+template <int N, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__ CUtensorMap tmap_v,
                   const __grid_constant__ CUtensorMap tmap_h32, const __grid_constant__ CUtensorMap tmap_v32, const ConvParams P) {
@@ -507,90 +748,50 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
     // stacks the row-axis taps (N, 2N or 3N columns: tile-edge rows feed fewer output rows).  The row loop
     // is fully unrolled so those shapes are compile-time; the wait for the NEXT stage is issued before the
     // last tap group of the current one so its latency hides behind queued tensor work.
-    const bool leader = ptx::elect_one() && !(P.flags & CF_DBG_NO_MMA);
-    const bool committer = ptx::elect_one();
-    const uint64_t adesc128 = ptx::smem_desc_sw128(a_smem, 1024, 0), bdesc128 = ptx::smem_desc_sw128(w_smem, 1024, 0);
-    const uint64_t adesc64 = ptx::smem_desc_sw64(a_smem, 512), bdesc64 = ptx::smem_desc_sw64(w_smem, 512);
-    const uint32_t full0 = ptx::smem_u32(&ctl->a_full[0]), empty0 = ptx::smem_u32(&ctl->a_empty[0]);
+    const bool elected = ptx::elect_one();
+    const bool do_mma = !(P.flags & CF_DBG_NO_MMA);
     const int n_my = tile0 < tile_end ? (tile_end - tile0 + tile_step - 1) / tile_step : 0;
-    const uint32_t idesc_base = P.idesc_base;
-    int stage = 0;
-    uint32_t aphase = 0, wcount = 0;
-    if (n_my > 0 && !ptx::mbar_wait_wd(full0, 0, wd)) tc_fail(P, 23);
-    for (int it = 0; it < n_my; it++) {
-      const int accbuf = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      if (!ptx::mbar_wait_wd(ptx::smem_u32(&ctl->t_empty[accbuf]), acc_phase ^ 1, wd)) tc_fail(P, 21);
-      if (P.trace && blockIdx.x == 0 && committer && it < 64) P.trace[it * 4 + 0] = clock64();
-      ptx::tc_fence_after();
-      const uint32_t acc_base = tmem_base + accbuf * R * N;
-      for (int c = 0; c < P.n_chunks; c++) {
-        const bool half_chunk = (P.cin - c * 64) < 64;  // 32 valid channels: 2 K-steps instead of 4
-        uint32_t wb;
-        if (!(P.w_resident && it > 0)) {
-          wb = wcount % P.n_wbuf;
-          if (!ptx::mbar_wait_wd(ptx::smem_u32(&ctl->w_full[wb]), (wcount / P.n_wbuf) & 1, wd)) tc_fail(P, 22);
-          wcount++;
-        } else {
-          wb = c;
-        }
-        ptx::tc_fence_after();
-        const uint64_t adesc0 = half_chunk ? adesc64 : adesc128;
-        const uint64_t bd = (half_chunk ? bdesc64 : bdesc128) + (uint64_t)((wb * P.w_chunk_bytes) >> 4);
-        const bool first_chunk = c == 0;
-#pragma unroll
-        for (int sp = 0; sp < (R + 2) / 2; sp++) {
-          const bool last = (sp == (R + 2) / 2 - 1) && (c == P.n_chunks - 1) && (it == n_my - 1);
-          const uint64_t ad0 = adesc0 + (uint64_t)(stage * (TC_ASTAGE >> 4));
-          int ns = stage + 1;
-          uint32_t np = aphase;
-          if (ns == P.n_stage) { ns = 0; np ^= 1; }
-#pragma unroll
-          for (int half = 0; half < 2; half++) {
-            const int yy = 2 * sp + half;                      // compile-time after unrolling
-            const int jlo = yy < 2 ? 2 - yy : 0;
-            const int jhi = R + 1 - yy < 2 ? R + 1 - yy : 2;
-            const uint32_t idesc = idesc_base | ((uint32_t)(((jhi - jlo + 1) * N) >> 3) << 17);
-            const uint32_t col = acc_base + (yy - 2 + jlo) * N;
-            // second row of the stage: 130 pixels further; operand rows are 128 B (full chunk) or 64 B (32-ch chunk)
-            const uint64_t ad = ad0 + (uint64_t)(half * (half_chunk ? (TC_ABYTES >> 5) : (TC_ABYTES >> 4)));
-            const uint64_t bj = bd + (uint64_t)(jlo * N * (half_chunk ? 4 : 8));
-            if (leader) {
-              if (half_chunk) issue_taps01<N, 2, 64>(first_chunk, acc_base, yy, jlo, jhi, col, ad, bd, bj, idesc, idesc_base);
-              else issue_taps01<N, 4, 128>(first_chunk, acc_base, yy, jlo, jhi, col, ad, bd, bj, idesc, idesc_base);
-            }
-            if (half == 1 && !last) {  // prefetch-wait for the next stage, hidden behind the MMAs queued above
-              if (!ptx::mbar_wait_wd(full0 + 8 * ns, np, wd)) tc_fail(P, 23);
-              ptx::tc_fence_after();
-            }
-            if (leader) {
-              if (half_chunk) mma_group<N, 2, 0, 2, 64>(col, ad, bj, idesc);
-              else mma_group<N, 2, 0, 4, 128>(col, ad, bj, idesc);
-            }
-          }
-          if (committer) ptx::mma_commit(empty0 + 8 * stage);
-          __syncwarp();
-          stage = ns;
-          aphase = np;
-        }
-        if (!P.w_resident && committer) ptx::mma_commit(ptx::smem_u32(&ctl->w_empty[wb]));
-      }
-      if (committer) ptx::mma_commit(ptx::smem_u32(&ctl->t_full[accbuf]));
-      if (P.trace && blockIdx.x == 0 && committer && it < 64) P.trace[it * 4 + 1] = clock64();
-      __syncwarp();
-    }
+#if WOWSR_VAR & 1
+    if (elected) mma_issuer<N, R, true>(P, ctl, do_mma, true, a_smem, w_smem, tmem_base, n_my);
+    __syncwarp();
+#else
+    mma_issuer<N, R, false>(P, ctl, elected && do_mma, elected, a_smem, w_smem, tmem_base, n_my);
+#endif
   } else {
     // ===================== epilogue warps (TMEM -> registers -> global) =====================
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int r_first = warp >> 2;      // two warps per quarter split the tile rows even / odd
     const int u_lim = vert ? P.h : P.w, v_lim = vert ? P.w : P.h;
+    const EpiConst E = make_epi_const(P);
+    const long long run_step = (vert ? (long long)P.w : 1LL) * E.out_stride;  // elements between pixels of a run
     for (int tile = tile0, it = 0; tile < tile_end; tile += tile_step, it++) {
       const TileCoord tc = decode_tile(P, vert, tile);
       const int n = tc.n, u = tc.u0 + q * 32 + lane;
       const int accbuf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+#if WOWSR_VAR & 8
+      // Pull this tile's fp32 residual blocks into L2 while the tensor pipe is still accumulating: a warp's 32 pixels
+      // x 64 channels of one tile row are ONE contiguous 8 KB block of the warp-blocked layout (64 lines, 2 per lane).
+      if (P.f32.wpb && (P.res1 || P.res2) && tc.u0 + q * 32 < u_lim) {
+        for (int r = r_first; r < R; r += TC_EPI_WARPS / 4) {
+          const int v = tc.v0 + r;
+          if (v >= v_lim) break;
+          const int u_blk = tc.u0 + q * 32;  // first pixel of the warp's block
+          const long long fb = f32_index(P.f32, P.h, n, vert ? u_blk : v, vert ? v : u_blk, 0) + lane * 32;
+          if (P.res1) { ptx::prefetch_l2(P.res1 + fb); ptx::prefetch_l2(P.res1 + fb + 1024); }
+          if (P.res2) { ptx::prefetch_l2(P.res2 + fb); ptx::prefetch_l2(P.res2 + fb + 1024); }
+        }
+      }
+#endif
+#if WOWSR_VAR & 4
+      long long e_ld = 0, e_rest = 0, e_n = 0;
+      const long long e_w0 = clock64();
+#endif
       if (!ptx::mbar_wait_wd(ptx::smem_u32(&ctl->t_full[accbuf]), acc_phase, wd)) tc_fail(P, 31);
       if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && it < 64) P.trace[it * 4 + 2] = clock64();
+#if WOWSR_VAR & 4
+      const long long e_w1 = clock64();
+#endif
       ptx::tc_fence_after();
       for (int r = r_first; r < R; r += TC_EPI_WARPS / 4) {
         const int v = tc.v0 + r;
@@ -601,14 +802,34 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
         if constexpr (N >= 32) {
           for (int c32 = 0; c32 < N / 32; c32++) {
             uint32_t rr[32];
+#if WOWSR_VAR & 4
+            const long long e0 = clock64();
+#endif
             ptx::tmem_ld32(taddr + c32 * 32, rr);
             ptx::tmem_ld_wait();
+#if WOWSR_VAR & 4
+            const long long e1 = clock64();
+#endif
             {
               float v[32];
 #pragma unroll
               for (int i = 0; i < 32; i++) v[i] = __uint_as_float(rr[i]);
-              epilogue_pixel<32, true>(P, n, y, x, c32 * 32, v, ctl->bias, valid, vert ? (long long)P.w : 1LL, u, u_lim);
+              if constexpr (MODE == EPI_GENERIC) {
+                epilogue_pixel<32, true>(P, n, y, x, c32 * 32, v, ctl->bias, valid, vert ? (long long)P.w : 1LL, u, u_lim);
+              } else {
+                uint16_t* px = E.out_t + (((long long)n * P.h + y) * P.w + x) * E.out_stride + c32 * 32;
+                if constexpr (MODE == EPI_PLAIN) {
+                  epi_plain32(E, v, ctl->bias + c32 * 32, px, run_step, u, u_lim);
+                } else {
+                  const long long fb = valid ? f32_index(P.f32, P.h, n, y, x, c32 * 32) : 0;
+                  epi_res32(E, v, ctl->bias + c32 * 32, fb, valid, px, run_step, u, u_lim);
+                }
+              }
             }
+#if WOWSR_VAR & 4
+            const long long e2 = clock64();
+            e_ld += e1 - e0; e_rest += e2 - e1; e_n++;
+#endif
           }
         } else {
           uint32_t rr[16];
@@ -626,6 +847,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&ctl->t_empty[accbuf]));
       if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && it < 64) P.trace[it * 4 + 3] = clock64();
+#if WOWSR_VAR & 4
+      if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && it < 64) {
+        P.trace[256 + it * 4 + 0] = e_ld; P.trace[256 + it * 4 + 1] = e_rest; P.trace[256 + it * 4 + 2] = e_n;
+        P.trace[256 + it * 4 + 3] = e_w1 - e_w0;
+      }
+#endif
     }
   }
   ptx::tc_fence_before();

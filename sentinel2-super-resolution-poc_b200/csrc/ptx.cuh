@@ -5,6 +5,12 @@
 #include <cuda.h>
 #include <stdint.h>
 
+// Compile-time experiment switches for the MMA issuer (tools/ab_bench.sh): bit 0 = single-lane issue loop,
+// bit 1 = spinning test_wait in the issuer's hot waits.
+#ifndef WOWSR_VAR
+#define WOWSR_VAR 0
+#endif
+
 namespace ptx {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -57,6 +63,30 @@ __device__ __forceinline__ bool mbar_wait_wd(uint32_t bar, uint32_t parity, uint
   budget = 4;
   return false;
 }
+
+// Hot-loop wait of the MMA issuer.  WOWSR_VAR bit 1: spin on the non-blocking test_wait instead of the parking
+// try_wait (a parked warp wakes late, and the tensor pipe only has ~2 MMAs queued to cover it).
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+               : "=r"(ok)
+               : "r"(bar), "r"(parity)
+               : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_wait_hot(uint32_t bar, uint32_t parity, uint32_t& budget) {
+#if WOWSR_VAR & 2
+#pragma unroll 1
+  for (uint32_t i = 0; i < (budget << 6); i++)
+    if (mbar_test_wait(bar, parity)) return true;
+  budget = 4;
+  return false;
+#else
+  return mbar_wait_wd(bar, parity, budget);
+#endif
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---- TMA ------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {

@@ -15,12 +15,19 @@ up.enhance_cuda(img); torch.cuda.synchronize()
 flags = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 up._h.set_option("tc_flags", flags)
 print("tc_flags", flags)
-for layer, name in [(11, "rdb.conv1"), (349, "conv_hr")]:
+for layer, name in [(11, "rdb.conv1"), (14, "rdb.conv4"), (15, "rdb.conv5"), (349, "conv_hr")]:
     up._h.set_option("tc_trace_layer", layer)
     up.enhance_cuda(img); torch.cuda.synchronize()
-    t = up._h.debug_trace()
+    t_all = up._h.debug_trace()
     up._h.set_option("tc_trace_layer", 0)
+    eb = t_all[64:128]
+    t = t_all[:64]
     t = t[(t != 0).all(1)]
+    eb = eb[eb[:, 2] > 0]
+    if len(eb):
+        it = eb[:, 2].astype(float)
+        print(f"   epilogue breakdown (warp 0, per 32-channel iteration): tmem_ld+wait {float((eb[:,0]/it).mean()):.0f} cyc, "
+              f"math+loads+stores {float((eb[:,1]/it).mean()):.0f} cyc, iterations/tile {it.mean():.1f}, wait for accumulators {float(eb[:,3].mean()):.0f} cyc/tile")
     t0 = t[0, 0]
     print(f"== {name} (launch {layer}): tile  mma_start  mma_issue_len  epi_start-mma_issued  epi_len  | next_mma_start - mma_start")
     for i in range(min(len(t), 4)):
