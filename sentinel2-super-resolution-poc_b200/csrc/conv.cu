@@ -35,7 +35,7 @@ struct ConvNet {
   float* first_w = nullptr;  // [ky][kx][ci][64] fp32
   float* first_b = nullptr;
   std::vector<LayerW> layers;
-  DevBuf dense0, dense1, feat, trunk, rrdb, up1, hra, hrb, wins, winxy, err;
+  DevBuf dense0, dense1, feat, trunk, rrdb, lo, up1, hra, hrb, wins, winxy, err;
 };
 
 void wowsr_net_free(ConvNet* n) {
@@ -48,7 +48,7 @@ void wowsr_net_free(ConvNet* n) {
   }
   if (n->first_w) cudaFree(n->first_w);
   if (n->first_b) cudaFree(n->first_b);
-  DevBuf* bufs[] = {&n->dense0, &n->dense1, &n->feat, &n->trunk, &n->rrdb, &n->up1, &n->hra, &n->hrb, &n->wins, &n->winxy, &n->err};
+  DevBuf* bufs[] = {&n->dense0, &n->dense1, &n->feat, &n->trunk, &n->rrdb, &n->lo, &n->up1, &n->hra, &n->hrb, &n->wins, &n->winxy, &n->err};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   delete n;
@@ -187,6 +187,9 @@ struct LayerIO {
   const float* res2 = nullptr;
   float* out_f32_a = nullptr;
   float* out_f32_b = nullptr;
+  const uint16_t* lo_in = nullptr;  // split trunk (see ConvParams)
+  uint16_t* lo_out = nullptr;
+  int ident = 0;
   void* out_t = nullptr;
   int out_stride = 0, out_choff = 0, out_rep = 1;
   int out_ps = 0;
@@ -217,7 +220,11 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
   P.flags = (int)wowsr_opt(ctx, "tc_flags", CF_STACK) | (L.fp16 ? CF_FP16 : 0) | (io.out_fp16 ? CF_OUT_FP16 : 0);
   P.idesc_base = make_idesc_f16(128, 0, L.fp16);
   P.w_chunk_bytes = (uint32_t)L.chunk_bytes;
-  size_t wtotal = L.chunk_bytes * L.n_chunks;
+  P.lo_in = io.lo_in; P.lo_out = io.lo_out; P.ident = io.ident;
+  if (P.ident && (N != 64 || L.cin < 64 || io.scale1 != 0.2f || !io.lo_in || io.res1))
+    return wowsr_fail(ctx, WOWSR_ERR_ARG, "identity K-step needs a 64-output layer, scale1 = 0.2 and a lo residual");
+  const size_t id_bytes = P.ident ? 8192 : 0;
+  size_t wtotal = L.chunk_bytes * L.n_chunks + id_bytes;
   if (wtotal + 2 * (size_t)TC_ASTAGE + SMEM_SLACK <= SMEM_LIMIT && L.n_chunks <= TC_MAX_WBUF &&
       !wowsr_opt(ctx, "tc_force_stream", 0)) {
     P.w_resident = 1;
@@ -226,7 +233,7 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
     P.w_resident = 0;
     P.n_wbuf = 2;
   }
-  size_t left = SMEM_LIMIT - SMEM_SLACK - (size_t)P.n_wbuf * L.chunk_bytes;
+  size_t left = SMEM_LIMIT - SMEM_SLACK - (size_t)P.n_wbuf * L.chunk_bytes - id_bytes;
   int stages = (int)(left / TC_ASTAGE);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   int64_t optS = wowsr_opt(ctx, "tc_stages", 0);
@@ -311,13 +318,13 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
       P.grid_h = grid - best;
     }
   }
-  size_t smem = (size_t)P.n_stage * TC_ASTAGE + (size_t)P.n_wbuf * L.chunk_bytes + SMEM_SLACK;
+  size_t smem = (size_t)P.n_stage * TC_ASTAGE + (size_t)P.n_wbuf * L.chunk_bytes + id_bytes + SMEM_SLACK;
   // epilogue specialisation (conv_kernels.cuh): the generic path handles every other layer shape
   int mode = EPI_GENERIC;
   if (!wowsr_opt(ctx, "tc_generic_epilogue", 0) && N >= 32 && !P.final && P.out_t && P.out_rep == 1 && !P.out_ps && !P.out_f32_b &&
       !(P.flags & CF_DBG_NO_STORE)) {
-    if (!P.res1 && !P.res2 && !P.out_f32_a) mode = EPI_PLAIN;
-    else if (N == 64 && P.f32.wpb && P.res1 && P.out_f32_a) mode = EPI_RES;
+    if (!P.res1 && !P.res2 && !P.out_f32_a && !P.lo_in && !P.lo_out) mode = EPI_PLAIN;
+    else if (N == 64 && P.f32.wpb && (P.res1 != nullptr) != (P.lo_in != nullptr) && (P.out_f32_a || P.lo_out)) mode = EPI_RES;
   }
   if (!ctx->tc_attr_set) {  // per device (one handle per device)
     WCUDA(ctx, cudaFuncSetAttribute(conv3x3_tc_kernel<16, EPI_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
@@ -372,7 +379,13 @@ int rrdbnet_batch(wowsr_ctx* ctx, ConvNet* net, const uint8_t* img, long long pi
   if (int e = wowsr_ensure(ctx, net->dense0, px * 192 * 2)) return e;
   if (int e = wowsr_ensure(ctx, net->dense1, px * 192 * 2)) return e;
   if (int e = wowsr_ensure(ctx, net->feat, pxb * 64 * 4)) return e;
-  if (int e = wowsr_ensure(ctx, net->trunk, pxb * 64 * 4)) return e;
+  // residual trunk inside an RRDB: split hi/lo (default) or a full fp32 copy (option trunk_hilo=0)
+  const bool hilo = wowsr_opt(ctx, "trunk_hilo", 1) != 0;
+  if (hilo) {
+    if (int e = wowsr_ensure(ctx, net->lo, pxb * 64 * 2)) return e;
+  } else {
+    if (int e = wowsr_ensure(ctx, net->trunk, pxb * 64 * 4)) return e;
+  }
   if (int e = wowsr_ensure(ctx, net->rrdb, pxb * 64 * 4)) return e;
   if (int e = wowsr_ensure(ctx, net->up1, px * 4 * 64 * 2)) return e;
   if (int e = wowsr_ensure(ctx, net->hra, px * 16 * 64 * 2)) return e;
@@ -421,9 +434,18 @@ int rrdbnet_batch(wowsr_ctx* ctx, ConvNet* net, const uint8_t* img, long long pi
       io.f32 = fl;
       // fp32 residual trunk without a separate copy of the RRDB input: T0 (`rrdb`) holds x_rrdb and stays
       // untouched while rdb1/rdb2 run on T1 (`trunk`); rdb3 reads both and writes the next RRDB's input to T0.
+      // Split trunk (default): rdb1 reads x_rrdb (fp32, T0) and leaves x1 as hi (operand copy in the next dense
+      // buffer) + lo (16-bit); rdb2 / rdb3 get hi through the identity K-step and read only lo; rdb3 writes T0.
       io.scale1 = 0.2f;
-      io.res1 = (const float*)(r == 0 ? net->rrdb.p : net->trunk.p);
-      io.out_f32_a = (float*)(r == 2 ? net->rrdb.p : net->trunk.p);
+      if (hilo) {
+        if (r == 0) io.res1 = (const float*)net->rrdb.p;
+        else { io.lo_in = (const uint16_t*)net->lo.p; io.ident = 1; }
+        if (r == 2) io.out_f32_a = (float*)net->rrdb.p;
+        else io.lo_out = (uint16_t*)net->lo.p;
+      } else {
+        io.res1 = (const float*)(r == 0 ? net->rrdb.p : net->trunk.p);
+        io.out_f32_a = (float*)(r == 2 ? net->rrdb.p : net->trunk.p);
+      }
       if (r == 2) {
         io.scale2 = 0.2f; io.res2 = (const float*)net->rrdb.p;
       }

@@ -71,6 +71,12 @@ __device__ __forceinline__ long long f32_index(const F32Layout& L, int h, int n,
   return L.strip_off + ((((long long)n * L.rem + (x - L.x0)) * L.hpb + (y >> 5)) * 64 + ch) * 32 + (y & 31) * 4;
 }
 
+// Same blocking for 16-bit data: a 32-pixel block stores [ch/8][pixel][ch%8] (16 bytes per lane and access).
+__device__ __forceinline__ long long lo_index(const F32Layout& L, int h, int n, int y, int x, int ch) {
+  if (x < L.x0) return ((((long long)n * h + y) * L.wpb + (x >> 5)) * 64 + ch) * 32 + (x & 31) * 8;
+  return L.strip_off + ((((long long)n * L.rem + (x - L.x0)) * L.hpb + (y >> 5)) * 64 + ch) * 32 + (y & 31) * 8;
+}
+
 struct ConvParams {
   int Nw, h, w;       // windows in the batch, layer resolution
   int cin, n_chunks;  // input channels (multiple of 16), 64-channel chunks
@@ -99,6 +105,13 @@ struct ConvParams {
   int out_stride, out_choff, out_rep;
   int out_ps;            // 1: depth-to-space(2) store: the chunk's channels are ordered [sub-pixel s][c]; s -> (2y+s/2, 2x+s%2)
   F32Layout f32;         // layout of the fp32 trunk buffers (wpb == 0: plain [pixel][64])
+  // Split residual trunk x = hi + lo (rdb.conv5): hi is the 16-bit operand copy in channels [0,64) of the dense buffer
+  // (which the next RDB reads anyway), lo = bf16(x - hi) in a warp-blocked 16-bit buffer.  Halves the trunk's HBM
+  // traffic against an fp32 copy; x is reproduced to ~2^-17 relative.
+  const uint16_t* lo_in; // residual 1 = hi + lo_in (res1 must be null)
+  uint16_t* lo_out;      // store v - hi(v) here
+  int ident;             // 1: the hi part of residual 1 is `in`[.., 0:64]; the tensor-core kernel adds it through an
+                         // identity K-step (B = 1/scale1 * I on the centre tap), the CUDA-core kernel reads it
   // final layer
   int final;
   float final_scale;     // u8 = quantise(v * final_scale + final_add[c]); RRDBNet: 255, 0, truncating; EDSR: 1, mean, rounding
@@ -159,6 +172,27 @@ __device__ __forceinline__ void epilogue_pixel(const ConvParams& P, int n, int y
   const long long pix = ((long long)n * P.h + y) * P.w + x;
   if (P.f32.wpb) {
     const long long fb = valid ? f32_index(P.f32, P.h, n, y, x, ch0) : 0;
+    const long long lb = valid ? lo_index(P.f32, P.h, n, y, x, ch0) : 0;
+    if (P.lo_in) {
+      const uint4* r = reinterpret_cast<const uint4*>(P.lo_in + lb);
+      const uint16_t* hp = reinterpret_cast<const uint16_t*>(P.in) + pix * P.in_stride + ch0;
+#pragma unroll
+      for (int i = 0; i < NCH / 8; i++) {
+        const uint4 t = valid ? r[i * 32] : make_uint4(0u, 0u, 0u, 0u);
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          float res = __uint_as_float((e & 1) ? (w[e >> 1] & 0xFFFF0000u) : (w[e >> 1] << 16));
+          if (!QUAD && P.ident && valid) {  // CUDA-core kernel: the hi part is read, not multiplied in
+            const uint16_t hv = hp[8 * i + e];
+            const float hf = (P.flags & CF_FP16) ? __half2float(*reinterpret_cast<const __half*>(&hv))
+                                                 : __uint_as_float((uint32_t)hv << 16);
+            res = __fadd_rn(hf, res);
+          }
+          v[8 * i + e] = __fadd_rn(__fmul_rn(v[8 * i + e], P.scale1), res);
+        }
+      }
+    }
     if (P.res1) {
       const float4* r = reinterpret_cast<const float4*>(P.res1 + fb);
       float4 t[NCH / 4];
@@ -199,6 +233,27 @@ __device__ __forceinline__ void epilogue_pixel(const ConvParams& P, int n, int y
       float4* o = reinterpret_cast<float4*>(P.out_f32_b + fb);
 #pragma unroll
       for (int i = 0; i < NCH / 4; i++) o[i * 32] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
+    if (P.lo_out && valid) {
+      uint4* o = reinterpret_cast<uint4*>(P.lo_out + lb);
+#pragma unroll
+      for (int i = 0; i < NCH / 8; i++) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          float h0, h1;
+          if (P.flags & CF_OUT_FP16) {
+            h0 = __half2float(__float2half_rn(v[8 * i + 2 * e]));
+            h1 = __half2float(__float2half_rn(v[8 * i + 2 * e + 1]));
+          } else {
+            h0 = __bfloat162float(__float2bfloat16_rn(v[8 * i + 2 * e]));
+            h1 = __bfloat162float(__float2bfloat16_rn(v[8 * i + 2 * e + 1]));
+          }
+          __nv_bfloat162 bb = __floats2bfloat162_rn(__fsub_rn(v[8 * i + 2 * e], h0), __fsub_rn(v[8 * i + 2 * e + 1], h1));
+          w[e] = *reinterpret_cast<uint32_t*>(&bb);
+        }
+        o[i * 32] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
     }
   } else if (valid) {
     if (P.res1) {
@@ -342,6 +397,8 @@ struct EpiConst {
   const float* res1;
   const float* res2;
   float* out_f32;
+  const uint16_t* lo_in;
+  uint16_t* lo_out;
 };
 
 __device__ __forceinline__ EpiConst make_epi_const(const ConvParams& P) {
@@ -357,6 +414,8 @@ __device__ __forceinline__ EpiConst make_epi_const(const ConvParams& P) {
   E.res1 = P.res1;
   E.res2 = P.res2;
   E.out_f32 = P.out_f32_a;
+  E.lo_in = P.lo_in;
+  E.lo_out = P.lo_out;
   return E;
 }
 
@@ -375,8 +434,7 @@ __device__ __forceinline__ void epi_bias32(float (&v)[32], const float* __restri
 // pack 32 fp32 values to 16-bit, transpose the 16-byte pieces inside lane quads and store: slot k of lane 4i+j ends
 // up holding piece j of pixel 4i+k, so each store instruction writes 64 contiguous bytes per quad.
 // `px` = address of channel ch0 of this lane's pixel; `step` = elements between consecutive pixels of the run.
-__device__ __forceinline__ void epi_store16_quad(const float (&v)[32], bool fp16, uint16_t* px, long long step, int u, int u_lim) {
-  uint32_t pk[16];
+__device__ __forceinline__ void epi_pack16(const float (&v)[32], bool fp16, uint32_t (&pk)[16]) {
   if (fp16) {
 #pragma unroll
     for (int i = 0; i < 16; i++) {
@@ -390,6 +448,8 @@ __device__ __forceinline__ void epi_store16_quad(const float (&v)[32], bool fp16
       pk[i] = *reinterpret_cast<uint32_t*>(&bb);
     }
   }
+}
+__device__ __forceinline__ void epi_store_quad(uint32_t (&pk)[16], uint16_t* px, long long step, int u, int u_lim) {
   const int j = threadIdx.x & 3;
 #pragma unroll
   for (int m = 1; m <= 2; m <<= 1) {
@@ -415,6 +475,11 @@ __device__ __forceinline__ void epi_store16_quad(const float (&v)[32], bool fp16
       *reinterpret_cast<uint4*>(base + (long long)d * step) = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
   }
 }
+__device__ __forceinline__ void epi_store16_quad(const float (&v)[32], bool fp16, uint16_t* px, long long step, int u, int u_lim) {
+  uint32_t pk[16];
+  epi_pack16(v, fp16, pk);
+  epi_store_quad(pk, px, step, u, u_lim);
+}
 
 __device__ __forceinline__ void epi_plain32(const EpiConst& E, float (&v)[32], const float* __restrict__ bias, uint16_t* px,
                                             long long step, int u, int u_lim) {
@@ -426,45 +491,74 @@ __device__ __forceinline__ void epi_plain32(const EpiConst& E, float (&v)[32], c
   epi_store16_quad(v, E.out_fp16, px, step, u, u_lim);
 }
 
-// `fb` = element index of channel ch0 of this lane's pixel in the warp-blocked fp32 buffers (f32_index)
-__device__ __forceinline__ void epi_res32(const EpiConst& E, float (&v)[32], const float* __restrict__ bias, long long fb, bool valid,
-                                          uint16_t* px, long long step, int u, int u_lim) {
-  float4 t[8];
-  {
+// `fb` / `lb` = element index of channel ch0 of this lane's pixel in the warp-blocked fp32 / 16-bit buffers
+__device__ __forceinline__ void epi_res32(const EpiConst& E, float (&v)[32], const float* __restrict__ bias, long long fb, long long lb,
+                                          bool valid, uint16_t* px, long long step, int u, int u_lim) {
+  float t[32];
+  if (E.lo_in) {  // hi part already in the accumulator (identity K-step); 4 x 16 bytes of bf16 lo
+    const uint4* r = reinterpret_cast<const uint4*>(E.lo_in + lb);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const uint4 w = valid ? r[i * 32] : make_uint4(0u, 0u, 0u, 0u);
+      t[8 * i + 0] = __uint_as_float(w.x << 16); t[8 * i + 1] = __uint_as_float(w.x & 0xFFFF0000u);
+      t[8 * i + 2] = __uint_as_float(w.y << 16); t[8 * i + 3] = __uint_as_float(w.y & 0xFFFF0000u);
+      t[8 * i + 4] = __uint_as_float(w.z << 16); t[8 * i + 5] = __uint_as_float(w.z & 0xFFFF0000u);
+      t[8 * i + 6] = __uint_as_float(w.w << 16); t[8 * i + 7] = __uint_as_float(w.w & 0xFFFF0000u);
+    }
+  } else {
     const float4* r = reinterpret_cast<const float4*>(E.res1 + fb);
 #pragma unroll
-    for (int i = 0; i < 8; i++) t[i] = valid ? r[i * 32] : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < 8; i++) {
+      const float4 w = valid ? r[i * 32] : make_float4(0.f, 0.f, 0.f, 0.f);
+      t[4 * i] = w.x; t[4 * i + 1] = w.y; t[4 * i + 2] = w.z; t[4 * i + 3] = w.w;
+    }
   }
   epi_bias32(v, bias);
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
-    v[4 * i + 0] = __fadd_rn(__fmul_rn(v[4 * i + 0], E.scale1), t[i].x);
-    v[4 * i + 1] = __fadd_rn(__fmul_rn(v[4 * i + 1], E.scale1), t[i].y);
-    v[4 * i + 2] = __fadd_rn(__fmul_rn(v[4 * i + 2], E.scale1), t[i].z);
-    v[4 * i + 3] = __fadd_rn(__fmul_rn(v[4 * i + 3], E.scale1), t[i].w);
-  }
+  for (int i = 0; i < 32; i++) v[i] = __fadd_rn(__fmul_rn(v[i], E.scale1), t[i]);
   if (E.has_res2) {
     const float4* r = reinterpret_cast<const float4*>(E.res2 + fb);
 #pragma unroll
-    for (int i = 0; i < 8; i++) t[i] = valid ? r[i * 32] : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
     for (int i = 0; i < 8; i++) {
-      v[4 * i + 0] = __fadd_rn(__fmul_rn(v[4 * i + 0], E.scale2), t[i].x);
-      v[4 * i + 1] = __fadd_rn(__fmul_rn(v[4 * i + 1], E.scale2), t[i].y);
-      v[4 * i + 2] = __fadd_rn(__fmul_rn(v[4 * i + 2], E.scale2), t[i].z);
-      v[4 * i + 3] = __fadd_rn(__fmul_rn(v[4 * i + 3], E.scale2), t[i].w);
+      const float4 w = valid ? r[i * 32] : make_float4(0.f, 0.f, 0.f, 0.f);
+      t[4 * i] = w.x; t[4 * i + 1] = w.y; t[4 * i + 2] = w.z; t[4 * i + 3] = w.w;
     }
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __fadd_rn(__fmul_rn(v[i], E.scale2), t[i]);
   }
   if (E.do_act) {
 #pragma unroll
     for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i], __fmul_rn(v[i], E.slope));
   }
-  if (valid) {
+  if (E.out_f32 && valid) {
     float4* o = reinterpret_cast<float4*>(E.out_f32 + fb);
 #pragma unroll
     for (int i = 0; i < 8; i++) o[i * 32] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
   }
-  epi_store16_quad(v, E.out_fp16, px, step, u, u_lim);
+  uint32_t pk[16];
+  epi_pack16(v, E.out_fp16, pk);
+  if (E.lo_out && valid) {
+    uint4* o = reinterpret_cast<uint4*>(E.lo_out + lb);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      uint32_t w[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        float h0, h1;
+        const uint32_t p = pk[4 * i + e];
+        if (E.out_fp16) {
+          const float2 hh = __half22float2(*reinterpret_cast<const __half2*>(&p));
+          h0 = hh.x; h1 = hh.y;
+        } else {
+          h0 = __uint_as_float(p << 16); h1 = __uint_as_float(p & 0xFFFF0000u);
+        }
+        __nv_bfloat162 bb = __floats2bfloat162_rn(__fsub_rn(v[8 * i + 2 * e], h0), __fsub_rn(v[8 * i + 2 * e + 1], h1));
+        w[e] = *reinterpret_cast<uint32_t*>(&bb);
+      }
+      o[i * 32] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+  epi_store_quad(pk, px, step, u, u_lim);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -509,9 +603,8 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& P, bool vert,
 // bases reach the uniform datapath once and every MMA costs two 64-bit adds (immediates are compile-time:
 // A advances 32 B per K-step and 128 B per tap; B 32 B per K-step and 3*N rows per tap; units of 16 B).
 // SW = bytes per operand row: 128 (64-channel chunk, SWIZZLE_128B) or 64 (32-channel remainder chunk, SWIZZLE_64B).
-template <int N, int KX, int KS0, int NK, int SW = 128>
-__device__ __forceinline__ void mma_group(uint32_t col, uint64_t a, uint64_t b, uint32_t idesc) {
-  constexpr int A0 = KX * (SW / 16) + KS0 * 2, B0 = KX * 3 * N * (SW / 16) + KS0 * 2;
+template <int A0, int B0, int NK>
+__device__ __forceinline__ void mma_group_raw(uint32_t col, uint64_t a, uint64_t b, uint32_t idesc) {
 #define WOWSR_MMA_STEP(IA, IB) \
   "add.u64 ta, %1, %" #IA ";\n\tadd.u64 tb, %2, %" #IB ";\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %3, p;\n\t"
 #define WOWSR_MMA_HEAD "{\n\t.reg .b64 ta, tb;\n\t.reg .pred p;\n\tsetp.eq.u32 p, 0, 0;\n\t"
@@ -533,6 +626,10 @@ __device__ __forceinline__ void mma_group(uint32_t col, uint64_t a, uint64_t b, 
   }
 #undef WOWSR_MMA_STEP
 #undef WOWSR_MMA_HEAD
+}
+template <int N, int KX, int KS0, int NK, int SW = 128>
+__device__ __forceinline__ void mma_group(uint32_t col, uint64_t a, uint64_t b, uint32_t idesc) {
+  mma_group_raw<KX * (SW / 16) + KS0 * 2, KX * 3 * N * (SW / 16) + KS0 * 2, NK>(col, a, b, idesc);
 }
 
 // First two run-axis taps of a stage.  `first_chunk`: the very first K-step of the tile must overwrite (not
@@ -566,10 +663,13 @@ struct IssueState {
 // NKS K-steps.  FIRST (first chunk of the tile: overwrite instead of accumulate) and HALF are compile-time so the
 // unrolled issue path carries no per-row branches.  SINGLE: the caller runs this on one elected lane only (no
 // warp-level reconvergence points between MMAs); otherwise the whole warp runs it and `leader` gates the issue.
-template <int N, int R, bool FIRST, bool HALF, bool SINGLE>
+// IDENT (first chunk only): after the taps of an input row that is also an output row, one more centre-tap K-sweep with
+// B = (1/scale1) * I adds the hi part of the residual trunk (channels [0,64) of this very chunk) to that row's accumulators.
+template <int N, int R, bool FIRST, bool HALF, bool SINGLE, bool IDENT = false>
 __device__ __forceinline__ void issue_chunk(const ConvParams& P, IssueState& S, bool leader, bool committer, bool last_chunk,
                                             uint32_t full0, uint32_t empty0, uint64_t adesc0, uint64_t bd, uint32_t acc_base,
-                                            uint32_t idesc_base) {
+                                            uint32_t idesc_base, uint64_t id_desc = 0) {
+  static_assert(!IDENT || (FIRST && !HALF && N == 64), "identity K-step: first full chunk of a 64-output layer");
   constexpr int NKS = HALF ? 2 : 4, SW = HALF ? 64 : 128;
 #pragma unroll
   for (int sp = 0; sp < (R + 2) / 2; sp++) {
@@ -594,6 +694,10 @@ __device__ __forceinline__ void issue_chunk(const ConvParams& P, IssueState& S, 
         ptx::tc_fence_after();
       }
       if (leader) mma_group<N, 2, 0, NKS, SW>(col, ad, bj, idesc);
+      if constexpr (IDENT) {
+        if (yy >= 1 && yy <= R && leader)  // centre tap: A shifted by one pixel (8 x 16 B), 4 K-steps, N = 64 into out row yy-1
+          mma_group_raw<8, 0, 4>(acc_base + (yy - 1) * N, ad, id_desc, idesc_base | ((uint32_t)(N >> 3) << 17));
+      }
     }
     if (committer) ptx::mma_commit(empty0 + 8 * S.stage);
     if constexpr (!SINGLE) __syncwarp();
@@ -605,7 +709,8 @@ __device__ __forceinline__ void issue_chunk(const ConvParams& P, IssueState& S, 
 // The MMA issuer role for all tiles of this CTA.
 template <int N, int R, bool SINGLE>
 __device__ __forceinline__ void mma_issuer(const ConvParams& P, TcSmemCtl* ctl, bool leader, bool committer, uint32_t a_smem,
-                                           uint32_t w_smem, uint32_t tmem_base, int n_my) {
+                                           uint32_t w_smem, uint32_t id_smem, uint32_t tmem_base, int n_my) {
+  const uint64_t id_desc = ptx::smem_desc_sw128(id_smem, 1024, 0);
   const uint64_t adesc128 = ptx::smem_desc_sw128(a_smem, 1024, 0), bdesc128 = ptx::smem_desc_sw128(w_smem, 1024, 0);
   const uint64_t adesc64 = ptx::smem_desc_sw64(a_smem, 512), bdesc64 = ptx::smem_desc_sw64(w_smem, 512);
   const uint32_t full0 = ptx::smem_u32(&ctl->a_full[0]), empty0 = ptx::smem_u32(&ctl->a_empty[0]);
@@ -635,8 +740,20 @@ __device__ __forceinline__ void mma_issuer(const ConvParams& P, TcSmemCtl* ctl, 
       const uint64_t bd = (half_chunk ? bdesc64 : bdesc128) + (uint64_t)((wb * P.w_chunk_bytes) >> 4);
       const bool last_chunk = (c == P.n_chunks - 1) && (it == n_my - 1);
       if (c == 0) {
-        if (half_chunk) issue_chunk<N, R, true, true, SINGLE>(P, S, leader, committer, last_chunk, full0, empty0, adesc0, bd, acc_base, idesc_base);
-        else issue_chunk<N, R, true, false, SINGLE>(P, S, leader, committer, last_chunk, full0, empty0, adesc0, bd, acc_base, idesc_base);
+        if (half_chunk) {
+          issue_chunk<N, R, true, true, SINGLE>(P, S, leader, committer, last_chunk, full0, empty0, adesc0, bd, acc_base, idesc_base);
+        } else {
+          bool done = false;
+          if constexpr (N == 64) {
+            if (P.ident) {
+              issue_chunk<N, R, true, false, SINGLE, true>(P, S, leader, committer, last_chunk, full0, empty0, adesc0, bd, acc_base,
+                                                            idesc_base, id_desc);
+              done = true;
+            }
+          }
+          if (!done)
+            issue_chunk<N, R, true, false, SINGLE>(P, S, leader, committer, last_chunk, full0, empty0, adesc0, bd, acc_base, idesc_base);
+        }
       } else {
         if (half_chunk) issue_chunk<N, R, false, true, SINGLE>(P, S, leader, committer, last_chunk, full0, empty0, adesc0, bd, acc_base, idesc_base);
         else issue_chunk<N, R, false, false, SINGLE>(P, S, leader, committer, last_chunk, full0, empty0, adesc0, bd, acc_base, idesc_base);
@@ -665,7 +782,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
   const uint32_t smem_base = (ptx::smem_u32(smem) + 1023u) & ~1023u;
   const uint32_t a_smem = smem_base;
   const uint32_t w_smem = a_smem + P.n_stage * TC_ASTAGE;
-  const uint32_t ctl_addr = w_smem + P.n_wbuf * P.w_chunk_bytes;
+  const uint32_t id_smem = w_smem + P.n_wbuf * P.w_chunk_bytes;  // 64 x 128 B identity operand (P.ident only)
+  const uint32_t ctl_addr = id_smem + (P.ident ? 8192u : 0u);
   TcSmemCtl* ctl = reinterpret_cast<TcSmemCtl*>(smem + (ctl_addr - ptx::smem_u32(smem)));
   constexpr int R = N == 64 ? 4 : 8;  // accumulator rows per tile: 2 (double buffer) x R x N = 512 TMEM columns
   const uint32_t tmem_cols = 2u * R * N <= 32 ? 32u : (2u * R * N <= 64 ? 64u : (2u * R * N <= 128 ? 128u : (2u * R * N <= 256 ? 256u : 512u)));
@@ -691,6 +809,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
     ptx::tmem_relinquish();
   }
   if (threadIdx.x < 64) ctl->bias[threadIdx.x] = (int)threadIdx.x < N ? P.bias[threadIdx.x] : 0.0f;
+  if (P.ident) {
+    // B = 5 * I (1 / 0.2, exact in bf16 and fp16) as a K-major SWIZZLE_128B operand: row co holds 5 at channel co
+    const uint32_t five = (P.flags & CF_FP16) ? 0x4500u : 0x40A0u;
+    uint32_t* idw = reinterpret_cast<uint32_t*>(smem + (id_smem - ptx::smem_u32(smem)));
+    for (int wd_i = threadIdx.x; wd_i < 2048; wd_i += TC_THREADS) {
+      const int row = wd_i >> 5, b = (wd_i & 31) * 4;
+      const int c0 = (((b >> 4) ^ (row & 7)) << 3) + ((b & 15) >> 1);  // logical channel of the word's low half
+      idw[wd_i] = (c0 == row ? five : 0u) | (c0 + 1 == row ? five << 16 : 0u);
+    }
+    ptx::fence_proxy_async();
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -752,10 +881,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
     const bool do_mma = !(P.flags & CF_DBG_NO_MMA);
     const int n_my = tile0 < tile_end ? (tile_end - tile0 + tile_step - 1) / tile_step : 0;
 #if WOWSR_VAR & 1
-    if (elected) mma_issuer<N, R, true>(P, ctl, do_mma, true, a_smem, w_smem, tmem_base, n_my);
+    if (elected) mma_issuer<N, R, true>(P, ctl, do_mma, true, a_smem, w_smem, id_smem, tmem_base, n_my);
     __syncwarp();
 #else
-    mma_issuer<N, R, false>(P, ctl, elected && do_mma, elected, a_smem, w_smem, tmem_base, n_my);
+    mma_issuer<N, R, false>(P, ctl, elected && do_mma, elected, a_smem, w_smem, id_smem, tmem_base, n_my);
 #endif
   } else {
     // ===================== epilogue warps (TMEM -> registers -> global) =====================
@@ -822,7 +951,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
                   epi_plain32(E, v, ctl->bias + c32 * 32, px, run_step, u, u_lim);
                 } else {
                   const long long fb = valid ? f32_index(P.f32, P.h, n, y, x, c32 * 32) : 0;
-                  epi_res32(E, v, ctl->bias + c32 * 32, fb, valid, px, run_step, u, u_lim);
+                  const long long lb = valid ? lo_index(P.f32, P.h, n, y, x, c32 * 32) : 0;
+                  epi_res32(E, v, ctl->bias + c32 * 32, fb, lb, valid, px, run_step, u, u_lim);
                 }
               }
             }
