@@ -106,6 +106,9 @@ class Handle:
         self._h = h
         self.device = int(device)
         self._keep = []
+        # a handle owns ONE workspace and stream set (include/wowsr.h): callers that share a handle between
+        # threads (the server caches loaded models across requests) serialise network calls on this lock
+        self.lock = threading.RLock()
 
     def close(self):
         if getattr(self, "_h", None):

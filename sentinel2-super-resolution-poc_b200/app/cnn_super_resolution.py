@@ -120,6 +120,36 @@ class RRDBNet(nn.Module):
         raise NotImplementedError("run the network through RealESRGAN.enhance(); the kernels take uint8 windows")
 
 
+# Loaded-model residency.  The reference constructs and deletes a ``RealESRGAN`` per request
+# (wow_sr.py:93,97; farm_sr.py:162): here that would re-read the .pth, rebuild 351 parameter tensors and
+# re-pack / re-upload 67 MB of weights every time.  Loaded models stay resident, keyed by what determines the
+# device image: (device, model, precision, weights identity).
+_MODEL_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
+_MODEL_CACHE_MAX = 4
+_cache_lock = __import__("threading").Lock()
+
+
+def _weights_fingerprint(state_dict=None, path=None):
+    if path is not None:
+        st = Path(path).stat()
+        return ("file", str(path), st.st_size, st.st_mtime_ns)
+    # cheap content fingerprint of an in-memory state dict: shapes plus a strided sample of every tensor
+    import hashlib
+    h = hashlib.blake2b(digest_size=16)
+    for k in sorted(state_dict):
+        t = torch.as_tensor(state_dict[k]).detach().reshape(-1)
+        h.update(k.encode())
+        h.update(str(tuple(t.shape)).encode())
+        h.update(t[:: max(1, t.numel() // 64)].float().cpu().numpy().tobytes())
+    return ("dict", h.hexdigest())
+
+
+def clear_model_cache():
+    """Drops every resident model (frees their device memory once no ``RealESRGAN`` refers to them)."""
+    with _cache_lock:
+        _MODEL_CACHE.clear()
+
+
 class RealESRGAN:
     """Real-ESRGAN inference wrapper with the reference's constructor and ``enhance`` (:161-234).
 
@@ -146,19 +176,40 @@ class RealESRGAN:
         self.scale = config["scale"]
         self.model_name = model_name
         self.precision = precision
-        self.model = RRDBNet(3, 3, config["channels"], config["blocks"], 32, self.scale)
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        weights_path = None
         if state_dict is None:
             weights_path = download_weights(model_name)
-            state_dict = torch.load(weights_path, map_location="cpu")
-        if "params_ema" in state_dict:
+        elif "params_ema" in state_dict:
             state_dict = state_dict["params_ema"]
         elif "params" in state_dict:
             state_dict = state_dict["params"]
+        key = None
+        if handle is None:
+            key = (dev_index, model_name, precision, _weights_fingerprint(state_dict, weights_path))
+            with _cache_lock:
+                hit = _MODEL_CACHE.get(key)
+                if hit is not None:
+                    _MODEL_CACHE.move_to_end(key)
+            if hit is not None:
+                self.model, self._h = hit
+                return
+        if state_dict is None:
+            state_dict = torch.load(weights_path, map_location="cpu")
+            if "params_ema" in state_dict:
+                state_dict = state_dict["params_ema"]
+            elif "params" in state_dict:
+                state_dict = state_dict["params"]
+        self.model = RRDBNet(3, 3, config["channels"], config["blocks"], 32, self.scale)
         self.model.load_state_dict(state_dict, strict=True)
         self.model.eval()
-        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self._h = handle if handle is not None else _lib.Handle(dev_index)
         self._h.load_rrdbnet(self.model.tensors(), config["blocks"], config["channels"], 32, precision)
+        if key is not None:
+            with _cache_lock:
+                _MODEL_CACHE[key] = (self.model, self._h)
+                while len(_MODEL_CACHE) > _MODEL_CACHE_MAX:
+                    _MODEL_CACHE.popitem(last=False)
 
     @torch.no_grad()
     def enhance(self, img: np.ndarray, outscale: int = 4) -> np.ndarray:
@@ -167,12 +218,14 @@ class RealESRGAN:
             raise ValueError(f"outscale={outscale} is not supported by {self.model_name} (x{self.scale})")
         if img.ndim != 3 or img.shape[2] != 3:
             raise ValueError("expected an HxWx3 image")
-        return self._h.enhance_host(np.asarray(img).astype(np.uint8, copy=False), self.tile_size)
+        with self._h.lock:
+            return self._h.enhance_host(np.asarray(img).astype(np.uint8, copy=False), self.tile_size)
 
     @torch.no_grad()
     def enhance_float(self, img: np.ndarray):
         """(uint8 output, float32 pre-quantisation output) — used by the parity tests."""
-        return self._h.enhance_host(np.asarray(img).astype(np.uint8, copy=False), self.tile_size, want_float=True)
+        with self._h.lock:
+            return self._h.enhance_host(np.asarray(img).astype(np.uint8, copy=False), self.tile_size, want_float=True)
 
     @torch.no_grad()
     def enhance_cuda(self, img: torch.Tensor) -> torch.Tensor:
@@ -180,8 +233,9 @@ class RealESRGAN:
         assert img.is_cuda and img.dtype == torch.uint8 and img.is_contiguous()
         H, W = img.shape[:2]
         out = torch.empty((4 * H, 4 * W, 3), dtype=torch.uint8, device=img.device)
-        self._h.enhance_dev(img.data_ptr(), H, W, self.tile_size, out.data_ptr(),
-                            stream=torch.cuda.current_stream(img.device).cuda_stream)
+        with self._h.lock:
+            self._h.enhance_dev(img.data_ptr(), H, W, self.tile_size, out.data_ptr(),
+                                stream=torch.cuda.current_stream(img.device).cuda_stream)
         return out
 
     def _tile_process(self, img):  # kept for interface parity; the planner + stitching are native

@@ -221,3 +221,30 @@ def test_window_independence_and_determinism(ws, handle):
     for q in wins:
         cover[4 * q.oy0:4 * q.oy1, 4 * q.ox0:4 * q.ox1] += 1
     assert (cover == 1).all()
+
+
+def test_kernel_option_paths_agree(ws):
+    """The specialised epilogues must be bit-identical to the generic one; the split (hi + lo) residual trunk must
+    agree with the fp32 trunk to ~2^-17 of the trunk (far below the operand rounding); the CUDA-core cross-check
+    kernel implements the same split."""
+    blocks = 2
+    sd = R.calibrate_conv_last(R.random_init_state_dict(4, blocks), blocks)
+    img = np.random.default_rng(12).integers(0, 256, (150, 276, 3), dtype=np.uint8)   # horizontal + vertical-strip tiles
+
+    def run(**opts):
+        h = ws.Handle(0)
+        for k, v in opts.items():
+            h.set_option(k, v)
+        h.load_rrdbnet(_tensors(sd, blocks), blocks, precision="bf16")
+        out = h.enhance_host(img, 256, want_float=True)
+        h.close()
+        return out
+
+    u8, f = run()
+    u8_g, f_g = run(tc_generic_epilogue=1)
+    assert np.array_equal(f, f_g) and np.array_equal(u8, u8_g)
+    u8_t, f_t = run(trunk_hilo=0)
+    assert np.abs(f - f_t).max() < 2e-4 * max(1.0, np.abs(f_t).max())
+    assert (np.abs(u8.astype(int) - u8_t.astype(int)) <= 1).all()
+    u8_s, f_s = run(conv_impl=1)
+    assert np.abs(f - f_s).max() < 2e-4 * max(1.0, np.abs(f_s).max())
