@@ -16,6 +16,8 @@ gloo to check the decomposition itself).
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -35,9 +37,14 @@ def split_rows(n: int, world: int):
 
 
 class ScenePlan:
-    """Window / band assignment of one rank for an H x W LR scene."""
+    """Window / band assignment of one rank for an H x W LR scene.
 
-    def __init__(self, H, W, tile, world, rank, scale=4, pad=10):
+    ``balance="rows"``: whole tile rows per rank (no SR exchange; 43 tile rows over 8 ranks leaves 6 vs 5 rows,
+    12 % imbalance).  ``balance="windows"`` (default): the row-major window list is cut into near-equal contiguous
+    ranges; a tile row cut between two ranks is post-processed by the rank that computes its first window, the other
+    rank ships its piece of that row's SR output (``pieces``) point-to-point before the CLAHE histogram."""
+
+    def __init__(self, H, W, tile, world, rank, scale=4, pad=10, balance="windows"):
         self.H, self.W, self.tile, self.world, self.rank, self.scale = H, W, tile, world, rank, scale
         wins = _lib.plan_windows(H, W, tile, pad)
         if len(wins) == 1:
@@ -46,7 +53,18 @@ class ScenePlan:
             tiles_x = (W + tile - 1) // tile
             tiles_y = (H + tile - 1) // tile
         self.tiles_y, self.tiles_x = tiles_y, tiles_x
-        self.row_bands = split_rows(tiles_y, world)
+        self.OH, self.OW = H * scale, W * scale
+        if balance == "rows" or len(wins) < 2 * world:
+            self.row_bands = split_rows(tiles_y, world)
+            self.win_ranges = [(r0 * tiles_x, r1 * tiles_x) for (r0, r1) in self.row_bands]
+        else:
+            self.win_ranges = split_rows(len(wins), world)
+            # tile row t belongs to the rank whose range holds its first window
+            self.row_bands = []
+            for (k0, k1) in self.win_ranges:
+                t0 = (k0 + tiles_x - 1) // tiles_x
+                t1 = (k1 + tiles_x - 1) // tiles_x
+                self.row_bands.append((min(t0, tiles_y), min(t1, tiles_y)))
         # output band [Y0, Y1) of every rank (output pixels)
         self.bands = []
         for (r0, r1) in self.row_bands:
@@ -56,10 +74,23 @@ class ScenePlan:
             else:
                 y0 = y1 = (self.bands[-1][1] if self.bands else 0)
             self.bands.append((y0, y1))
-        r0, r1 = self.row_bands[rank]
-        self.windows = wins[r0 * tiles_x:r1 * tiles_x]
+        k0, k1 = self.win_ranges[rank]
+        self.windows = wins[k0:k1]
         self.Y0, self.Y1 = self.bands[rank]
-        self.OH, self.OW = H * scale, W * scale
+        # output rows this rank's windows write (a superset of its band when rows are cut between ranks)
+        self.SY0 = min((w.oy0 for w in self.windows), default=0) * scale
+        self.SY1 = max((w.oy1 for w in self.windows), default=0) * scale
+        # SR pieces computed by one rank and post-processed by another: (src, dst, y0, y1, x0, x1) in output pixels
+        self.pieces = []
+        for src, (a, b) in enumerate(self.win_ranges):
+            t = a // tiles_x if b > a else 0
+            while b > a and t * tiles_x < b:
+                c0, c1 = max(a, t * tiles_x), min(b, (t + 1) * tiles_x)
+                dst = next(r for r, (r0, r1) in enumerate(self.row_bands) if r0 <= t < r1)
+                if dst != src and c1 > c0:
+                    self.pieces.append((src, dst, wins[c0].oy0 * scale, wins[c0].oy1 * scale, wins[c0].ox0 * scale,
+                                        wins[c1 - 1].ox1 * scale))
+                t += 1
 
     def neighbours(self):
         """Ranks holding the band directly above / below this one (skipping empty bands)."""
@@ -117,21 +148,39 @@ class GpuBackend:
         return torch.zeros(self.params.grid ** 2 * 256, dtype=torch.int32, device=self.dev)
 
 
-def run_scene(backend, img, tile, post=True, gather=True, group=None):
+def run_scene(backend, img, tile, post=True, gather=True, group=None, balance="windows"):
     """One pass of the sharded pipeline.  `img`: HxWx3 uint8 tensor on the backend's device (every rank holds
     the LR scene; it is 1/16 of the output).  Returns (plan, local post-processed band, full image on rank 0
     or None)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     H, W = img.shape[:2]
-    plan = ScenePlan(H, W, tile, world, rank)
+    plan = ScenePlan(H, W, tile, world, rank, balance=balance)
     r = backend.blur_radius() if post else 0
-    have = plan.Y1 > plan.Y0
-    lo = max(plan.Y0 - r, 0) if have else 0
-    hi = min(plan.Y1 + r, plan.OH) if have else 0
+    have = plan.Y1 > plan.Y0            # owns an output band
+    have_win = len(plan.windows) > 0     # computes SR windows
+    lo = max(plan.Y0 - r, 0) if have else plan.SY0
+    hi = min(plan.Y1 + r, plan.OH) if have else plan.SY1
+    if have_win:
+        lo, hi = min(lo, plan.SY0), max(hi, plan.SY1)
     band = backend.new_band(max(hi - lo, 1), plan.OW)
-    if have:
+    if have_win:
         backend.sr_band(img, plan, band, lo)
+    # (1b) tile rows cut between two ranks: ship the SR pieces to the rank that post-processes the row
+    mine = [p for p in plan.pieces if p[0] == rank or p[1] == rank]
+    if mine:
+        ops, pastes = [], []
+        for (src, dst, y0, y1, x0, x1) in mine:
+            if src == rank:
+                ops.append(dist.P2POp(dist.isend, band[y0 - lo:y1 - lo, x0:x1].contiguous(), dst, group))
+            else:
+                buf = backend.new_band(y1 - y0, x1 - x0)
+                ops.append(dist.P2POp(dist.irecv, buf, src, group))
+                pastes.append((buf, y0, y1, x0, x1))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        for (buf, y0, y1, x0, x1) in pastes:
+            band[y0 - lo:y1 - lo, x0:x1] = buf
     if not post:
         out = band[plan.Y0 - lo:plan.Y1 - lo] if have else band[:0]
     else:
@@ -150,10 +199,10 @@ def run_scene(backend, img, tile, post=True, gather=True, group=None):
             ops = []
             if have and up is not None:
                 ops.append(dist.P2POp(dist.isend, band[plan.Y0 - lo:plan.Y0 - lo + r].contiguous(), up, group))
-                ops.append(dist.P2POp(dist.irecv, band[0:plan.Y0 - lo], up, group))
+                ops.append(dist.P2POp(dist.irecv, band[plan.Y0 - r - lo:plan.Y0 - lo], up, group))
             if have and dn is not None:
                 ops.append(dist.P2POp(dist.isend, band[plan.Y1 - lo - r:plan.Y1 - lo].contiguous(), dn, group))
-                ops.append(dist.P2POp(dist.irecv, band[plan.Y1 - lo:hi - lo], dn, group))
+                ops.append(dist.P2POp(dist.irecv, band[plan.Y1 - lo:plan.Y1 + r - lo], dn, group))
             if ops:
                 for req in dist.batch_isend_irecv(ops):
                     req.wait()
@@ -176,3 +225,56 @@ def run_scene(backend, img, tile, post=True, gather=True, group=None):
             elif have:
                 dist.send(out.contiguous(), 0, group=group)
     return plan, out, full
+
+
+class SharedHostImage:
+    """Host-side result buffer shared by the ranks of ONE box (POSIX shared memory, page-locked in every process).
+
+    The NVLink gather above leaves the whole stitched image on rank 0, whose single PCIe link then carries all of it to
+    the host (5.8 GB for a Sentinel-2 scene).  When the consumer is host code (the server writes PNG / GeoTIFF files),
+    every rank instead copies its own band device->host into this buffer over its own PCIe link, in parallel."""
+
+    def __init__(self, OH, OW, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.nbytes = OH * OW * 3
+        name = [f"/dev/shm/wowsr_{os.getpid()}_{OH}x{OW}"] if self.rank == 0 else [None]
+        if self.world > 1:
+            dist.broadcast_object_list(name, src=0, group=group)
+        self.path = name[0]
+        if self.rank == 0:
+            self.array = torch.from_file(self.path, shared=True, size=self.nbytes, dtype=torch.uint8)
+        if self.world > 1:
+            dist.barrier(group)
+        if self.rank != 0:
+            self.array = torch.from_file(self.path, shared=True, size=self.nbytes, dtype=torch.uint8)
+        self.array = self.array.view(OH, OW, 3)
+        self.pinned = False
+        if torch.cuda.is_available():
+            self.pinned = int(torch.cuda.cudart().cudaHostRegister(self.array.data_ptr(), self.nbytes, 0) or 0) == 0
+
+    def close(self):
+        if getattr(self, "array", None) is None:
+            return
+        if self.pinned:
+            torch.cuda.cudart().cudaHostUnregister(self.array.data_ptr())
+        self.array = None
+        if self.world > 1:
+            dist.barrier(self.group)
+        if self.rank == 0 and os.path.exists(self.path):
+            os.unlink(self.path)
+
+
+def run_scene_to_host(backend, host_img, tile, shared: SharedHostImage, post=True, balance="windows"):
+    """Host-to-host pass: `host_img` (pinned HxWx3 uint8) -> device, sharded pipeline, every rank's band -> `shared`.
+    On return (after the closing barrier) ``shared.array`` holds the complete image in every process."""
+    d = host_img.to(getattr(backend, "dev", "cpu"), non_blocking=True)
+    plan, out, _ = run_scene(backend, d, tile, post=post, gather=False, group=shared.group, balance=balance)
+    if plan.Y1 > plan.Y0:
+        shared.array[plan.Y0:plan.Y1].copy_(out, non_blocking=True)
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    if shared.world > 1:
+        dist.barrier(shared.group)
+    return plan

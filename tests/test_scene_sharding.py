@@ -111,7 +111,7 @@ def _expected(img, tile, params):
     return P.post_process(out, pp)
 
 
-def _worker(rank, world, port, H, W, tile, kind, q):
+def _worker(rank, world, port, H, W, tile, kind, q, balance="windows"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import importlib
@@ -120,7 +120,14 @@ def _worker(rank, world, port, H, W, tile, kind, q):
     params = ws._lib.post_params(kind)
     rng = np.random.default_rng(5)
     img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
-    plan, band, full = scene.run_scene(OracleBackend(params, ws._lib), torch.from_numpy(img), tile, post=True, gather=True)
+    if balance == "shared_host":   # every rank writes its band into one shared host image (no gather on rank 0)
+        shared = scene.SharedHostImage(4 * H, 4 * W)
+        plan = scene.run_scene_to_host(OracleBackend(params, ws._lib), torch.from_numpy(img), tile, shared)
+        full = shared.array.clone()
+        shared.close()
+    else:
+        plan, band, full = scene.run_scene(OracleBackend(params, ws._lib), torch.from_numpy(img), tile, post=True, gather=True,
+                                           balance=balance)
     if rank == 0:
         want = _expected(img, tile, params)
         q.put((bool(np.array_equal(full.numpy(), want)), [tuple(b) for b in plan.bands]))
@@ -136,12 +143,14 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world,H,W,tile,kind", [(2, 70, 50, 16, "wow"), (3, 70, 50, 16, "farm"), (2, 37, 45, 64, "wow")])
-def test_sharded_scene_equals_single_process(world, H, W, tile, kind):
+@pytest.mark.parametrize("world,H,W,tile,kind,balance", [(2, 70, 50, 16, "wow", "windows"), (3, 70, 50, 16, "farm", "windows"),
+                                                         (2, 37, 45, 64, "wow", "windows"), (3, 70, 50, 16, "wow", "rows"),
+                                                         (3, 40, 90, 16, "wow", "windows"), (2, 70, 50, 16, "wow", "shared_host")])
+def test_sharded_scene_equals_single_process(world, H, W, tile, kind, balance):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, H, W, tile, kind, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, H, W, tile, kind, q, balance)) for r in range(world)]
     for p in procs:
         p.start()
     ok, bands = q.get(timeout=240)
@@ -158,11 +167,17 @@ def test_split_rows_and_plan():
     scene = importlib.import_module("sentinel2-super-resolution-poc_b200.scene")
     assert scene.split_rows(43, 8) == [(0, 6), (6, 12), (12, 18), (18, 23), (23, 28), (28, 33), (33, 38), (38, 43)]
     assert scene.split_rows(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
-    total = 0
-    for r in range(8):
-        p = scene.ScenePlan(10980, 10980, 256, 8, r)
-        total += len(p.windows)
-        assert p.Y1 > p.Y0
-    assert total == 1849
+    for balance, spread in (("rows", 43), ("windows", 1)):
+        total, counts = 0, []
+        for r in range(8):
+            p = scene.ScenePlan(10980, 10980, 256, 8, r, balance=balance)
+            total += len(p.windows)
+            counts.append(len(p.windows))
+            assert p.Y1 > p.Y0
+        assert total == 1849 and max(counts) - min(counts) <= spread, (balance, counts)
+    p = scene.ScenePlan(10980, 10980, 256, 8, 3)
+    # every cut tile row is shipped exactly once, to the rank that owns the row
+    assert len(p.pieces) == 7 and all(src != dst for (src, dst, *_rest) in p.pieces)
+    assert p.bands[0][0] == 0 and p.bands[-1][1] == 43920 and all(p.bands[i][1] == p.bands[i + 1][0] for i in range(7))
     p = scene.ScenePlan(100, 100, 256, 4, 2)          # untiled image: rank 0 does everything
     assert len(p.windows) == 0 and p.Y0 == p.Y1

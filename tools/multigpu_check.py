@@ -42,8 +42,17 @@ def main():
             want = fn(sr.contiguous())
             same = bool(torch.equal(full, want))
             ok_all &= same
-            print(f"[multigpu_check] {H}x{W} {kind} world={world} bands={plan.bands} equal_to_single_gpu={same}", flush=True)
+            print(f"[multigpu_check] {H}x{W} {kind} world={world} bands={plan.bands} pieces={len(plan.pieces)} "
+                  f"equal_to_single_gpu={same}", flush=True)
         dist.barrier()
+        # host-to-host variant: every rank copies its band into one shared page-locked host image
+        shared = scene.SharedHostImage(4 * H, 4 * W)
+        scene.run_scene_to_host(backend, torch.from_numpy(img).pin_memory(), 256, shared)
+        if rank == 0:
+            same = bool(torch.equal(shared.array, want.cpu()))
+            ok_all &= same
+            print(f"[multigpu_check] {H}x{W} {kind} shared host image (pinned={shared.pinned}) equal_to_single_gpu={same}", flush=True)
+        shared.close()
     if rank == 0:
         print("[multigpu_check] " + ("PASS" if ok_all else "FAIL"), flush=True)
     dist.destroy_process_group()
