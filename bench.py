@@ -268,7 +268,9 @@ def run_ours(args):
 
     # end-to-end through the public API with host buffers (rank-local scene at N>1 is the same call)
     e2e = None
-    if tile > 0:
+    if args.no_e2e:
+        pass
+    elif tile > 0:
         shared = None
         if world > 1:
             try:  # every rank copies its band to the host over its own PCIe link (scene.SharedHostImage)
@@ -373,6 +375,7 @@ def main():
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"])
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiler passes only; such a line is not a bench value)")
     ap.add_argument("--opt", action="append", default=[], help="libwowsr option key=value")
     args = ap.parse_args()
     if args.impl == "reference":

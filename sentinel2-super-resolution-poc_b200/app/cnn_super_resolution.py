@@ -125,7 +125,7 @@ class RRDBNet(nn.Module):
 # re-pack / re-upload 67 MB of weights every time.  Loaded models stay resident, keyed by what determines the
 # device image: (device, model, precision, weights identity).
 _MODEL_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
-_MODEL_CACHE_MAX = 4
+_MODEL_CACHE_MAX = 2  # each resident model owns a workspace sized by its largest batch (up to mem_budget_mb)
 _cache_lock = __import__("threading").Lock()
 
 

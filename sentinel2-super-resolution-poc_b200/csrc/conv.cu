@@ -219,6 +219,7 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
   P.n_tiles = P.tiles_x * P.tiles_y * io.Nw;
   P.flags = (int)wowsr_opt(ctx, "tc_flags", CF_STACK) | (L.fp16 ? CF_FP16 : 0) | (io.out_fp16 ? CF_OUT_FP16 : 0);
   P.idesc_base = make_idesc_f16(128, 0, L.fp16);
+  P.reverse = wowsr_opt(ctx, "tc_boustrophedon", 0) ? (int)(ctx->launches & 1) : 0;
   P.w_chunk_bytes = (uint32_t)L.chunk_bytes;
   P.lo_in = io.lo_in; P.lo_out = io.lo_out; P.ident = io.ident;
   if (P.ident && (N != 64 || L.cin < 64 || io.scale1 != 0.2f || !io.lo_in || io.res1))

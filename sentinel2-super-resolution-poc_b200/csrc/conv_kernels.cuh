@@ -84,6 +84,8 @@ struct ConvParams {
   int R, tiles_x, tiles_y, n_tiles;  // horizontal tiles: runs per row, row blocks, total
   int grid_h, strip_x0, v_runs, v_rows, n_tiles_v;  // vertical tiles of the remainder strip (n_tiles_v = 0: none)
   int flags;
+  int reverse;          // walk the tile list backwards (alternate launches: the next layer starts where this one ended,
+                        // on the ~100 MB of activations still in L2)
   uint32_t idesc_base;  // instruction descriptor with N = 0
   int w_resident, n_wbuf, n_stage;
   uint32_t w_chunk_bytes;
@@ -590,6 +592,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& P, bool vert,
   TileCoord t;
   const int runs = vert ? P.v_runs : P.tiles_x, rows = vert ? P.v_rows : P.tiles_y;
   const int per_win = runs * rows;
+  if (P.reverse) tile = (vert ? P.n_tiles_v : P.n_tiles) - 1 - tile;
   t.n = tile / per_win;
   const int tr = tile - t.n * per_win;
   const int vb = tr / runs, ur = tr - vb * runs;
