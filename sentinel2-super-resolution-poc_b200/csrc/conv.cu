@@ -21,6 +21,9 @@ struct LayerW {
   bool fp16 = false;  // operand type of this layer (input activations and weights)
   uint8_t* wpack = nullptr;
   uint8_t* wpack_v = nullptr;  // taps transposed, for vertical tiles
+  uint8_t* wpack32 = nullptr;  // same as [chunk of 32 ch][kx][j][co][32ch] (SWIZZLE_64B rows): layers whose weights are streamed
+  uint8_t* wpack32_v = nullptr;
+  size_t chunk_bytes32 = 0;
   float* wsimple = nullptr;
   float* bias = nullptr;
 };
@@ -43,6 +46,8 @@ void wowsr_net_free(ConvNet* n) {
   for (auto& l : n->layers) {
     if (l.wpack) cudaFree(l.wpack);
     if (l.wpack_v) cudaFree(l.wpack_v);
+    if (l.wpack32) cudaFree(l.wpack32);
+    if (l.wpack32_v) cudaFree(l.wpack32_v);
     if (l.wsimple) cudaFree(l.wsimple);
     if (l.bias) cudaFree(l.bias);
   }
@@ -114,6 +119,36 @@ int upload_layer(wowsr_ctx* ctx, LayerW& L, const float* w, const float* b, int 
         for (int co = 0; co < cout; co++)
           simple[((size_t)(ky * 3 + kx) * cin + ci) * N + co] =
               from_t(to_t(w[(((size_t)co * cin + ci) * 3 + ky) * 3 + kx], fp16), fp16);
+  // layers whose weights do not fit beside two activation stages are streamed per chunk; 32-channel chunks halve the
+  // double buffer (run_conv picks the mode with the same test)
+  // Measured (profiles/r01_epilogue_breakdown.txt, exp9): -4 % cycles per rdb.conv5 tile but no time gain under the
+  // power cap, so the mode is opt-in (option tc_chunk32=1 before loading the network).
+  if (wowsr_opt(ctx, "tc_chunk32", 0) && L.chunk_bytes * L.n_chunks + 2 * (size_t)TC_ASTAGE + SMEM_SLACK > SMEM_LIMIT) {
+    L.chunk_bytes32 = (size_t)3 * 3 * N * 64;
+    const int nc32 = cin / 32;
+    std::vector<uint8_t> p32(L.chunk_bytes32 * nc32, 0), p32v(L.chunk_bytes32 * nc32, 0);
+    for (int c = 0; c < nc32; c++)
+      for (int a = 0; a < 3; a++)
+        for (int j = 0; j < 3; j++) {
+          const int bt = 2 - j;
+          for (int co = 0; co < cout; co++) {
+            const int row = j * N + co;
+            for (int ch = 0; ch < 32; ch++) {
+              const int ci = c * 32 + ch;
+              const size_t off = (size_t)c * L.chunk_bytes32 + (size_t)a * (3 * N * 64) + (size_t)row * 64 +
+                                 (size_t)(((ch >> 3) ^ ((row >> 1) & 3)) << 4) + (size_t)(ch & 7) * 2;
+              const uint16_t th = to_t(w[(((size_t)co * cin + ci) * 3 + bt) * 3 + a], fp16);
+              const uint16_t tv = to_t(w[(((size_t)co * cin + ci) * 3 + a) * 3 + bt], fp16);
+              memcpy(&p32[off], &th, 2);
+              memcpy(&p32v[off], &tv, 2);
+            }
+          }
+        }
+    WCUDA(ctx, cudaMalloc((void**)&L.wpack32, p32.size()));
+    WCUDA(ctx, cudaMalloc((void**)&L.wpack32_v, p32v.size()));
+    WCUDA(ctx, cudaMemcpy(L.wpack32, p32.data(), p32.size(), cudaMemcpyHostToDevice));
+    WCUDA(ctx, cudaMemcpy(L.wpack32_v, p32v.data(), p32v.size(), cudaMemcpyHostToDevice));
+  }
   std::vector<float> bias(64, 0.0f);
   for (int co = 0; co < cout; co++) bias[co] = b ? b[co] : 0.0f;
   WCUDA(ctx, cudaMalloc((void**)&L.wpack, pack.size()));
@@ -226,22 +261,33 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
     return wowsr_fail(ctx, WOWSR_ERR_ARG, "identity K-step needs a 64-output layer, scale1 = 0.2 and a lo residual");
   const size_t id_bytes = P.ident ? 8192 : 0;
   size_t wtotal = L.chunk_bytes * L.n_chunks + id_bytes;
+  size_t chunk_bytes = L.chunk_bytes;
+  P.chunk_ch = 64;
+  P.astage = TC_ASTAGE;
   if (wtotal + 2 * (size_t)TC_ASTAGE + SMEM_SLACK <= SMEM_LIMIT && L.n_chunks <= TC_MAX_WBUF &&
       !wowsr_opt(ctx, "tc_force_stream", 0)) {
     P.w_resident = 1;
     P.n_wbuf = L.n_chunks;
   } else {
     P.w_resident = 0;
-    P.n_wbuf = 2;
+    P.n_wbuf = (int)wowsr_opt(ctx, "tc_wbuf", 2);
+    if (P.n_wbuf < 2 || P.n_wbuf > TC_MAX_WBUF) P.n_wbuf = 2;
+    if (L.wpack32 && wowsr_opt(ctx, "tc_chunk32", 0)) {  // streamed weights: 32-channel chunks, half-size stage slots
+      P.chunk_ch = 32;
+      P.astage = TC_ASTAGE32;
+      P.n_chunks = L.cin / 32;
+      chunk_bytes = L.chunk_bytes32;
+      P.w_chunk_bytes = (uint32_t)chunk_bytes;
+    }
   }
-  size_t left = SMEM_LIMIT - SMEM_SLACK - (size_t)P.n_wbuf * L.chunk_bytes - id_bytes;
-  int stages = (int)(left / TC_ASTAGE);
+  size_t left = SMEM_LIMIT - SMEM_SLACK - (size_t)P.n_wbuf * chunk_bytes - id_bytes;
+  int stages = (int)(left / P.astage);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   int64_t optS = wowsr_opt(ctx, "tc_stages", 0);
   if (optS > 0 && optS < stages) stages = (int)optS;
   if (stages < 2) return wowsr_fail(ctx, WOWSR_ERR_UNSUPPORTED, "not enough shared memory for conv %d->%d", L.cin, L.cout);
   P.n_stage = stages;
-  P.wpack = L.wpack; P.wsimple = L.wsimple; P.bias = L.bias;
+  P.wpack = P.chunk_ch == 32 ? L.wpack32 : L.wpack; P.wsimple = L.wsimple; P.bias = L.bias;
   P.in = io.in; P.in_stride = io.in_C;
   P.act = io.act; P.scale1 = io.scale1; P.res1 = io.res1; P.scale2 = io.scale2; P.res2 = io.res2;
   P.out_f32_a = io.out_f32_a; P.out_f32_b = io.out_f32_b;
@@ -275,7 +321,7 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
   CUtensorMap tmap, tmap_v, tmap32, tmap_v32;
   if (int e = make_tmap(ctx, &tmap, io.in, io.in_C, io.w, io.h, io.Nw, L.fp16, false)) return e;
   tmap_v = tmap;
-  const bool has_half = L.cin % 64 == 32;  // remainder chunk of 32 channels: its own 32-channel / SWIZZLE_64B maps
+  const bool has_half = L.cin % 64 == 32 || P.chunk_ch == 32;  // 32-channel chunks: their own 32-channel / SWIZZLE_64B maps
   tmap32 = tmap;
   if (has_half)
     if (int e = make_tmap(ctx, &tmap32, io.in, io.in_C, io.w, io.h, io.Nw, L.fp16, false, true)) return e;
@@ -299,7 +345,7 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
       P.n_tiles_v = v_runs * v_rows * io.Nw;
       P.tiles_x = wm / TC_RUN;
       P.n_tiles = P.tiles_x * P.tiles_y * io.Nw;
-      P.wpack_v = L.wpack_v;
+      P.wpack_v = P.chunk_ch == 32 ? L.wpack32_v : L.wpack_v;
     }
   }
   int grid = P.n_tiles + P.n_tiles_v < max_grid ? P.n_tiles + P.n_tiles_v : max_grid;
@@ -319,7 +365,7 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
       P.grid_h = grid - best;
     }
   }
-  size_t smem = (size_t)P.n_stage * TC_ASTAGE + (size_t)P.n_wbuf * L.chunk_bytes + id_bytes + SMEM_SLACK;
+  size_t smem = (size_t)P.n_stage * P.astage + (size_t)P.n_wbuf * chunk_bytes + id_bytes + SMEM_SLACK;
   // epilogue specialisation (conv_kernels.cuh): the generic path handles every other layer shape
   int mode = EPI_GENERIC;
   if (!wowsr_opt(ctx, "tc_generic_epilogue", 0) && N >= 32 && !P.final && P.out_t && P.out_rep == 1 && !P.out_ps && !P.out_f32_b &&

@@ -36,7 +36,8 @@ constexpr int TC_RUN = 128;           // output pixels per M-run
 constexpr int TC_AROWS = TC_RUN + 2;  // input pixels per row stage
 constexpr int TC_ABYTES = TC_AROWS * 128;
 constexpr int TC_ASTAGE = 33792;      // one pipeline stage = two input rows (2 * TC_ABYTES rounded up to 1024)
-constexpr int TC_MAX_STAGES = 10;
+constexpr int TC_ASTAGE32 = 17408;    // same for 32-channel chunks (2 * 130 * 64 B rounded up to 1024)
+constexpr int TC_MAX_STAGES = 12;
 constexpr int TC_MAX_WBUF = 4;
 
 constexpr int CF_STACK = 1;    // stack the three ky taps along N
@@ -79,7 +80,10 @@ __device__ __forceinline__ long long lo_index(const F32Layout& L, int h, int n, 
 
 struct ConvParams {
   int Nw, h, w;       // windows in the batch, layer resolution
-  int cin, n_chunks;  // input channels (multiple of 16), 64-channel chunks
+  int cin, n_chunks;  // input channels (multiple of 32), K chunks
+  int chunk_ch;       // channels per chunk: 64, or 32 for layers whose weights are streamed (halves the weight double
+                      // buffer, which buys 4x more activation stages in flight: rdb.conv5 was starved with 2 stages)
+  int astage;         // bytes of one activation stage slot (TC_ASTAGE / TC_ASTAGE32)
   int N, cout;        // padded / real output channels
   int R, tiles_x, tiles_y, n_tiles;  // horizontal tiles: runs per row, row blocks, total
   int grid_h, strip_x0, v_runs, v_rows, n_tiles_v;  // vertical tiles of the remainder strip (n_tiles_v = 0: none)
@@ -672,12 +676,12 @@ template <int N, int R, bool FIRST, bool HALF, bool SINGLE, bool IDENT = false>
 __device__ __forceinline__ void issue_chunk(const ConvParams& P, IssueState& S, bool leader, bool committer, bool last_chunk,
                                             uint32_t full0, uint32_t empty0, uint64_t adesc0, uint64_t bd, uint32_t acc_base,
                                             uint32_t idesc_base, uint64_t id_desc = 0) {
-  static_assert(!IDENT || (FIRST && !HALF && N == 64), "identity K-step: first full chunk of a 64-output layer");
+  static_assert(!IDENT || N == 64, "identity K-step: 64-output layers only");
   constexpr int NKS = HALF ? 2 : 4, SW = HALF ? 64 : 128;
 #pragma unroll
   for (int sp = 0; sp < (R + 2) / 2; sp++) {
     const bool last = (sp == (R + 2) / 2 - 1) && last_chunk;
-    const uint64_t ad0 = adesc0 + (uint64_t)(S.stage * (TC_ASTAGE >> 4));
+    const uint64_t ad0 = adesc0 + (uint64_t)(S.stage * (P.astage >> 4));
     int ns = S.stage + 1;
     uint32_t np = S.aphase;
     if (ns == P.n_stage) { ns = 0; np ^= 1; }
@@ -698,8 +702,8 @@ __device__ __forceinline__ void issue_chunk(const ConvParams& P, IssueState& S, 
       }
       if (leader) mma_group<N, 2, 0, NKS, SW>(col, ad, bj, idesc);
       if constexpr (IDENT) {
-        if (yy >= 1 && yy <= R && leader)  // centre tap: A shifted by one pixel (8 x 16 B), 4 K-steps, N = 64 into out row yy-1
-          mma_group_raw<8, 0, 4>(acc_base + (yy - 1) * N, ad, id_desc, idesc_base | ((uint32_t)(N >> 3) << 17));
+        if (yy >= 1 && yy <= R && leader)  // centre tap: A shifted by one pixel (one operand row), N = 64 into out row yy-1
+          mma_group_raw<SW / 16, 0, NKS>(acc_base + (yy - 1) * N, ad, id_desc, idesc_base | ((uint32_t)(N >> 3) << 17));
       }
     }
     if (committer) ptx::mma_commit(empty0 + 8 * S.stage);
@@ -713,7 +717,7 @@ __device__ __forceinline__ void issue_chunk(const ConvParams& P, IssueState& S, 
 template <int N, int R, bool SINGLE>
 __device__ __forceinline__ void mma_issuer(const ConvParams& P, TcSmemCtl* ctl, bool leader, bool committer, uint32_t a_smem,
                                            uint32_t w_smem, uint32_t id_smem, uint32_t tmem_base, int n_my) {
-  const uint64_t id_desc = ptx::smem_desc_sw128(id_smem, 1024, 0);
+  const uint64_t id_desc = ptx::smem_desc_sw128(id_smem, 1024, 0), id_desc64 = ptx::smem_desc_sw64(id_smem, 512);
   const uint64_t adesc128 = ptx::smem_desc_sw128(a_smem, 1024, 0), bdesc128 = ptx::smem_desc_sw128(w_smem, 1024, 0);
   const uint64_t adesc64 = ptx::smem_desc_sw64(a_smem, 512), bdesc64 = ptx::smem_desc_sw64(w_smem, 512);
   const uint32_t full0 = ptx::smem_u32(&ctl->a_full[0]), empty0 = ptx::smem_u32(&ctl->a_empty[0]);
@@ -729,7 +733,7 @@ __device__ __forceinline__ void mma_issuer(const ConvParams& P, TcSmemCtl* ctl, 
     ptx::tc_fence_after();
     const uint32_t acc_base = tmem_base + accbuf * R * N;
     for (int c = 0; c < P.n_chunks; c++) {
-      const bool half_chunk = (P.cin - c * 64) < 64;  // 32 valid channels: 2 K-steps instead of 4
+      const bool half_chunk = P.chunk_ch == 32 || (P.cin - c * 64) < 64;  // 32 channels: 2 K-steps instead of 4
       uint32_t wb;
       if (!(P.w_resident && it > 0)) {
         wb = wcount % P.n_wbuf;
@@ -742,25 +746,24 @@ __device__ __forceinline__ void mma_issuer(const ConvParams& P, TcSmemCtl* ctl, 
       const uint64_t adesc0 = half_chunk ? adesc64 : adesc128;
       const uint64_t bd = (half_chunk ? bdesc64 : bdesc128) + (uint64_t)((wb * P.w_chunk_bytes) >> 4);
       const bool last_chunk = (c == P.n_chunks - 1) && (it == n_my - 1);
-      if (c == 0) {
-        if (half_chunk) {
-          issue_chunk<N, R, true, true, SINGLE>(P, S, leader, committer, last_chunk, full0, empty0, adesc0, bd, acc_base, idesc_base);
+      // the chunks holding input channels [0,64) also carry the identity K-step (hi part of the residual trunk)
+      const bool ident = N == 64 && P.ident && c * P.chunk_ch < 64;
+      const uint64_t idd = half_chunk ? id_desc64 + (uint64_t)(c * (4096 >> 4)) : id_desc;
+#define WOWSR_CHUNK(F, H, I) \
+  issue_chunk<N, R, F, H, SINGLE, I>(P, S, leader, committer, last_chunk, full0, empty0, adesc0, bd, acc_base, idesc_base, idd)
+      if constexpr (N == 64) {
+        if (ident) {
+          if (c == 0) { if (half_chunk) WOWSR_CHUNK(true, true, true); else WOWSR_CHUNK(true, false, true); }
+          else { if (half_chunk) WOWSR_CHUNK(false, true, true); else WOWSR_CHUNK(false, false, true); }
         } else {
-          bool done = false;
-          if constexpr (N == 64) {
-            if (P.ident) {
-              issue_chunk<N, R, true, false, SINGLE, true>(P, S, leader, committer, last_chunk, full0, empty0, adesc0, bd, acc_base,
-                                                            idesc_base, id_desc);
-              done = true;
-            }
-          }
-          if (!done)
-            issue_chunk<N, R, true, false, SINGLE>(P, S, leader, committer, last_chunk, full0, empty0, adesc0, bd, acc_base, idesc_base);
+          if (c == 0) { if (half_chunk) WOWSR_CHUNK(true, true, false); else WOWSR_CHUNK(true, false, false); }
+          else { if (half_chunk) WOWSR_CHUNK(false, true, false); else WOWSR_CHUNK(false, false, false); }
         }
       } else {
-        if (half_chunk) issue_chunk<N, R, false, true, SINGLE>(P, S, leader, committer, last_chunk, full0, empty0, adesc0, bd, acc_base, idesc_base);
-        else issue_chunk<N, R, false, false, SINGLE>(P, S, leader, committer, last_chunk, full0, empty0, adesc0, bd, acc_base, idesc_base);
+        if (c == 0) { if (half_chunk) WOWSR_CHUNK(true, true, false); else WOWSR_CHUNK(true, false, false); }
+        else { if (half_chunk) WOWSR_CHUNK(false, true, false); else WOWSR_CHUNK(false, false, false); }
       }
+#undef WOWSR_CHUNK
       if (!P.w_resident && committer) ptx::mma_commit(ptx::smem_u32(&ctl->w_empty[wb]));
     }
     if (committer) ptx::mma_commit(ptx::smem_u32(&ctl->t_full[accbuf]));
@@ -784,7 +787,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
   const int tile_end = vert ? P.n_tiles_v : P.n_tiles;
   const uint32_t smem_base = (ptx::smem_u32(smem) + 1023u) & ~1023u;
   const uint32_t a_smem = smem_base;
-  const uint32_t w_smem = a_smem + P.n_stage * TC_ASTAGE;
+  const uint32_t w_smem = a_smem + P.n_stage * P.astage;
   const uint32_t id_smem = w_smem + P.n_wbuf * P.w_chunk_bytes;  // 64 x 128 B identity operand (P.ident only)
   const uint32_t ctl_addr = id_smem + (P.ident ? 8192u : 0u);
   TcSmemCtl* ctl = reinterpret_cast<TcSmemCtl*>(smem + (ctl_addr - ptx::smem_u32(smem)));
@@ -817,8 +820,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
     const uint32_t five = (P.flags & CF_FP16) ? 0x4500u : 0x40A0u;
     uint32_t* idw = reinterpret_cast<uint32_t*>(smem + (id_smem - ptx::smem_u32(smem)));
     for (int wd_i = threadIdx.x; wd_i < 2048; wd_i += TC_THREADS) {
-      const int row = wd_i >> 5, b = (wd_i & 31) * 4;
-      const int c0 = (((b >> 4) ^ (row & 7)) << 3) + ((b & 15) >> 1);  // logical channel of the word's low half
+      int row, c0;  // operand row (output channel) and logical input channel of the word's low half
+      if (P.chunk_ch == 64) {  // one 64 x 128 B tile, SWIZZLE_128B: 16-byte unit ^ row % 8
+        row = wd_i >> 5;
+        const int b = (wd_i & 31) * 4;
+        c0 = (((b >> 4) ^ (row & 7)) << 3) + ((b & 15) >> 1);
+      } else {                 // two 64 x 64 B tiles (input channels 0..31 / 32..63), SWIZZLE_64B: unit ^ (row / 2) % 4
+        const int t = wd_i >> 10, w = wd_i & 1023;
+        row = w >> 4;
+        const int b = (w & 15) * 4;
+        c0 = 32 * t + (((b >> 4) ^ ((row >> 1) & 3)) << 3) + ((b & 15) >> 1);
+      }
       idw[wd_i] = (c0 == row ? five : 0u) | (c0 + 1 == row ? five << 16 : 0u);
     }
     ptx::fence_proxy_async();
@@ -851,7 +863,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
             if (P.flags & CF_DBG_NO_TMA) {
               ptx::mbar_arrive(ptx::smem_u32(&ctl->w_full[b]));
             } else {
-              const uint32_t wbytes = (P.cin - c * 64) < 64 ? P.w_chunk_bytes / 2 : P.w_chunk_bytes;
+              const uint32_t wbytes = (P.chunk_ch == 64 && (P.cin - c * 64) < 64) ? P.w_chunk_bytes / 2 : P.w_chunk_bytes;
               ptx::mbar_arrive_expect_tx(ptx::smem_u32(&ctl->w_full[b]), wbytes);
               ptx::bulk_load(w_smem + b * P.w_chunk_bytes, wpack + (size_t)c * P.w_chunk_bytes, wbytes, ptx::smem_u32(&ctl->w_full[b]));
             }
@@ -864,9 +876,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_const
             if (P.flags & CF_DBG_NO_TMA) {
               ptx::mbar_arrive(ptx::smem_u32(&ctl->a_full[stage]));
             } else {
-              const bool half_c = (P.cin - c * 64) < 64;
+              const bool half_c = P.chunk_ch == 32 || (P.cin - c * 64) < 64;
               ptx::mbar_arrive_expect_tx(ptx::smem_u32(&ctl->a_full[stage]), half_c ? TC_ABYTES : 2 * TC_ABYTES);
-              ptx::tma_load_4d(a_smem + stage * TC_ASTAGE, half_c ? &tmap32 : &tmap, ptx::smem_u32(&ctl->a_full[stage]), c * 64,
+              ptx::tma_load_4d(a_smem + stage * P.astage, half_c ? &tmap32 : &tmap, ptx::smem_u32(&ctl->a_full[stage]), c * P.chunk_ch,
                                tc.u0 - 1, tc.v0 - 1 + 2 * sp, tc.n);
             }
           }
