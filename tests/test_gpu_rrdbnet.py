@@ -252,3 +252,5 @@ def test_kernel_option_paths_agree(ws):
     assert (np.abs(u8.astype(int) - u8_t.astype(int)) <= 1).mean() >= 0.999
     u8_s, f_s = run(conv_impl=1)
     assert np.abs(f - f_s).max() < tol
+    u8_c, f_c = run(tc_chunk32=1)      # rdb.conv5 streamed in 32-channel chunks (other K order, identity K-step per half)
+    assert np.abs(f - f_c).max() < tol and np.abs(f_c - ref_f).max() < 4 * tol
