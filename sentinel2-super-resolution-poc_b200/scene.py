@@ -227,17 +227,32 @@ def run_scene(backend, img, tile, post=True, gather=True, group=None, balance="w
     return plan, out, full
 
 
+def _clear_cuda_error():
+    """A failed cudaHostRegister leaves its error code as the runtime's 'last error'; the next PyTorch launch check
+    would raise it.  Reading it resets it."""
+    import ctypes
+    for name in ("libcudart.so.12", "libcudart.so.13", "libcudart.so"):
+        try:
+            ctypes.CDLL(name).cudaGetLastError()
+            return
+        except OSError:
+            continue
+
+
 class SharedHostImage:
-    """Host-side result buffer shared by the ranks of ONE box (POSIX shared memory, page-locked in every process).
+    """Host-side result buffer shared by the ranks of ONE box (POSIX shared memory).
 
     The NVLink gather above leaves the whole stitched image on rank 0, whose single PCIe link then carries all of it to
     the host (5.8 GB for a Sentinel-2 scene).  When the consumer is host code (the server writes PNG / GeoTIFF files),
-    every rank instead copies its own band device->host into this buffer over its own PCIe link, in parallel."""
+    every rank instead copies its own band device->host into this buffer over its own PCIe link, in parallel.  Each
+    rank page-locks only the rows it writes (``pin_rows``): registering the whole image in every process multiplies the
+    locked-page accounting by the world size and fails for large scenes (cudaErrorOperatingSystem at 8 x 6.4 GB)."""
 
     def __init__(self, OH, OW, group=None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.OH, self.OW = OH, OW
         self.nbytes = OH * OW * 3
         name = [f"/dev/shm/wowsr_{os.getpid()}_{OH}x{OW}"] if self.rank == 0 else [None]
         if self.world > 1:
@@ -250,15 +265,38 @@ class SharedHostImage:
         if self.rank != 0:
             self.array = torch.from_file(self.path, shared=True, size=self.nbytes, dtype=torch.uint8)
         self.array = self.array.view(OH, OW, 3)
+        self._range = None
         self.pinned = False
-        if torch.cuda.is_available():
-            self.pinned = int(torch.cuda.cudart().cudaHostRegister(self.array.data_ptr(), self.nbytes, 0) or 0) == 0
+
+    def pin_rows(self, y0, y1):
+        """Page-locks the (page-aligned) byte range of rows [y0, y1); returns False (and copies stay pageable) on failure."""
+        if not torch.cuda.is_available() or y1 <= y0:
+            return False
+        base, row = self.array.data_ptr(), self.OW * 3
+        a = (base + y0 * row) & ~4095
+        b = min((base + y1 * row + 4095) & ~4095, (base + self.nbytes + 4095) & ~4095)
+        if self._range == (a, b):
+            return True
+        self._unpin()
+        rc = torch.cuda.cudart().cudaHostRegister(a, b - a, 0)
+        if rc is not None and int(rc) != 0:
+            _clear_cuda_error()
+            self.pinned = False
+            return False
+        self._range, self.pinned = (a, b), True
+        return True
+
+    def _unpin(self):
+        if self._range is not None:
+            rc = torch.cuda.cudart().cudaHostUnregister(self._range[0])
+            if rc is not None and int(rc) != 0:
+                _clear_cuda_error()
+            self._range, self.pinned = None, False
 
     def close(self):
         if getattr(self, "array", None) is None:
             return
-        if self.pinned:
-            torch.cuda.cudart().cudaHostUnregister(self.array.data_ptr())
+        self._unpin()
         self.array = None
         if self.world > 1:
             dist.barrier(self.group)
@@ -272,6 +310,7 @@ def run_scene_to_host(backend, host_img, tile, shared: SharedHostImage, post=Tru
     d = host_img.to(getattr(backend, "dev", "cpu"), non_blocking=True)
     plan, out, _ = run_scene(backend, d, tile, post=post, gather=False, group=shared.group, balance=balance)
     if plan.Y1 > plan.Y0:
+        shared.pin_rows(plan.Y0, plan.Y1)
         shared.array[plan.Y0:plan.Y1].copy_(out, non_blocking=True)
     if torch.cuda.is_available():
         torch.cuda.synchronize()

@@ -47,6 +47,12 @@ def main():
         dist.barrier()
         # host-to-host variant: every rank copies its band into one shared page-locked host image
         shared = scene.SharedHostImage(4 * H, 4 * W)
+        if rank == 0:   # a failing registration (same range twice) must not poison later CUDA calls
+            shared.pin_rows(0, 8)
+            rc = torch.cuda.cudart().cudaHostRegister(shared._range[0], shared._range[1] - shared._range[0], 0)
+            assert int(rc) != 0
+            scene._clear_cuda_error()
+            torch.zeros(4, device=dev).sum().item()
         scene.run_scene_to_host(backend, torch.from_numpy(img).pin_memory(), 256, shared)
         if rank == 0:
             same = bool(torch.equal(shared.array, want.cpu()))
