@@ -87,9 +87,9 @@ class ScenePlan:
             while b > a and t * tiles_x < b:
                 c0, c1 = max(a, t * tiles_x), min(b, (t + 1) * tiles_x)
                 dst = next(r for r, (r0, r1) in enumerate(self.row_bands) if r0 <= t < r1)
-                if dst != src and c1 > c0:
-                    self.pieces.append((src, dst, wins[c0].oy0 * scale, wins[c0].oy1 * scale, wins[c0].ox0 * scale,
-                                        wins[c1 - 1].ox1 * scale))
+                piece = (src, dst, wins[c0].oy0 * scale, wins[c0].oy1 * scale, wins[c0].ox0 * scale, wins[c1 - 1].ox1 * scale)
+                if dst != src and piece[3] > piece[2] and piece[5] > piece[4]:  # windows can own nothing (image < tile + 2 pad)
+                    self.pieces.append(piece)
                 t += 1
 
     def neighbours(self):

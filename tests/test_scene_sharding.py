@@ -181,3 +181,42 @@ def test_split_rows_and_plan():
     assert p.bands[0][0] == 0 and p.bands[-1][1] == 43920 and all(p.bands[i][1] == p.bands[i + 1][0] for i in range(7))
     p = scene.ScenePlan(100, 100, 256, 4, 2)          # untiled image: rank 0 does everything
     assert len(p.windows) == 0 and p.Y0 == p.Y1
+
+
+def test_scene_plan_properties():
+    """Host logic of the window-balanced sharding, over many scene shapes and world sizes: every window is computed
+    exactly once; bands are contiguous, ordered and cover the output; every tile row cut between ranks is shipped, as
+    one rectangle per (source, row), to the rank that owns the row, and those rectangles plus the owner's own windows
+    cover the owner's band exactly once."""
+    import importlib
+    from hypothesis import given, settings, strategies as st
+    scene = importlib.import_module("sentinel2-super-resolution-poc_b200.scene")
+
+    @settings(max_examples=120, deadline=None)
+    @given(st.integers(20, 700), st.integers(20, 700), st.sampled_from([16, 32, 64, 100, 256]), st.integers(1, 8))
+    def check(H, W, tile, world):
+        plans = [scene.ScenePlan(H, W, tile, world, r) for r in range(world)]
+        p0 = plans[0]
+        all_w = [(w.x0, w.y0) for p in plans for w in p.windows]
+        import wowsr_b200 as ws
+        ref = [(w.x0, w.y0) for w in ws._lib.plan_windows(H, W, tile)]
+        assert all_w == ref                                              # contiguous ranges in row-major order, no gaps
+        assert p0.bands[0][0] == 0 and p0.bands[-1][1] == 4 * H
+        assert all(p0.bands[i][1] == p0.bands[i + 1][0] for i in range(world - 1))
+        assert all(p.pieces == p0.pieces for p in plans)                 # every rank derives the same exchange list
+        for r, p in enumerate(plans):
+            cover = np.zeros((p.Y1 - p.Y0, 4 * W), np.int32)
+            for w in p.windows:                                          # own windows inside the own band
+                y0, y1 = max(4 * w.oy0, p.Y0), min(4 * w.oy1, p.Y1)
+                if y1 > y0:
+                    cover[y0 - p.Y0:y1 - p.Y0, 4 * w.ox0:4 * w.ox1] += 1
+            for (src, dst, y0, y1, x0, x1) in p0.pieces:
+                assert src != dst
+                if dst == r:
+                    assert p.Y0 <= y0 and y1 <= p.Y1
+                    cover[y0 - p.Y0:y1 - p.Y0, x0:x1] += 1
+                if src == r:                                             # shipped rows are rows this rank computed
+                    assert p.SY0 <= y0 and y1 <= p.SY1 and not (p.Y0 <= y0 and y1 <= p.Y1 and p.Y1 > p.Y0)
+            assert (cover == 1).all(), (H, W, tile, world, r)
+
+    check()
