@@ -254,9 +254,20 @@ class SharedHostImage:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.OH, self.OW = OH, OW
         self.nbytes = OH * OW * 3
-        name = [f"/dev/shm/wowsr_{os.getpid()}_{OH}x{OW}"] if self.rank == 0 else [None]
+        name = [None]
+        if self.rank == 0:
+            # tmpfs pages are allocated on first touch: a too-small /dev/shm would kill the writers with SIGBUS, so check
+            # the free space up front and let EVERY rank fail the same way (callers fall back to the rank-0 gather)
+            try:
+                st = os.statvfs("/dev/shm")
+                if st.f_bavail * st.f_frsize >= self.nbytes + (256 << 20):
+                    name = [f"/dev/shm/wowsr_{os.getpid()}_{OH}x{OW}"]
+            except OSError:
+                pass
         if self.world > 1:
             dist.broadcast_object_list(name, src=0, group=group)
+        if name[0] is None:
+            raise OSError(f"/dev/shm cannot hold a {self.nbytes >> 20} MiB image")
         self.path = name[0]
         if self.rank == 0:
             self.array = torch.from_file(self.path, shared=True, size=self.nbytes, dtype=torch.uint8)

@@ -72,3 +72,22 @@ def test_against_unmodified_reference_classes():
     up = refload.make_upsampler(cnn, m, tile_size=16)
     img = np.random.default_rng(1).integers(0, 256, (50, 70, 3), dtype=np.uint8)
     assert np.array_equal(up.enhance(img), R.enhance(sd, img, 2, 16))
+
+
+def test_split_trunk_representation_bound():
+    """the residual trunk is stored as hi + lo with hi = bf16(x) and lo = bf16(x - hi).  Host-side
+    restatement of that arithmetic: x is reproduced to 2^-17 relative (two 8-bit significands plus the sign of lo), x - hi is exact in fp32,
+    and 5 * hi (the identity K-step's product, 1/0.2) is exact in fp32."""
+    import torch
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1 << 16, generator=g) * torch.logspace(-3, 3, 1 << 16)
+    hi = x.to(torch.bfloat16).float()
+    d = x - hi
+    assert torch.equal(d.double(), x.double() - hi.double())                 # Sterbenz-style exactness of the difference
+    lo = d.to(torch.bfloat16).float()
+    err = (x.double() - (hi.double() + lo.double())).abs()
+    assert float((err / x.double().abs()).max()) <= 2.0 ** -17
+    assert torch.equal((5.0 * hi).double(), 5.0 * hi.double())               # 8-bit significand x 3-bit constant
+    # (acc + 5*hi) * 0.2f reproduces hi to fp32 rounding: 5 * fl(0.2) = 1 + 1.5e-8
+    back = (5.0 * hi) * torch.tensor(0.2, dtype=torch.float32)
+    assert float(((back - hi).abs() / hi.abs().clamp_min(1e-30)).max()) <= 2.0 ** -23
