@@ -238,6 +238,37 @@ __device__ __forceinline__ uint32_t vegetation_pixel(int r, int g, int b, bool t
   return (uint32_t)clampi(ri, 0, 255) | ((uint32_t)clampi(gi, 0, 255) << 8) | ((uint32_t)clampi(bi, 0, 255) << 16);
 }
 
+// Stage-1 arithmetic of one halo pixel: RGB -> Lab (A.1), CLAHE bilinear LUT interpolation on L (A.2), Lab -> RGB (A.3).
+__device__ __forceinline__ uint32_t enhance_px(const uint8_t* __restrict__ p, bool do_clahe, const SmemTabs& T,
+                                               const uint8_t* __restrict__ lut1, const uint8_t* __restrict__ lut2, int ctx1,
+                                               int ctx2, float cxa, float cxa1, float ya, float ya1) {
+  const int cr = __ldg(p), cg = __ldg(p + 1), cb = __ldg(p + 2);
+  if (!do_clahe) return (uint32_t)cr | ((uint32_t)cg << 8) | ((uint32_t)cb << 16);
+  // RGB -> Lab (A.1)
+  const int R = T.gam[cr], G = T.gam[cg], B = T.gam[cb];
+  const int fX = T.cbrt[ds(1777 * R + 1541 * G + 778 * B, 12)];
+  const int fY = T.cbrt[ds(871 * R + 2929 * G + 296 * B, 12)];
+  const int fZ = T.cbrt[ds(73 * R + 448 * G + 3575 * B, 12)];
+  int L = clampi(ds(296 * fY - 1336934, 15), 0, 255);
+  const int a = clampi(ds(500 * (fX - fY) + 128 * 32768, 15), 0, 255);
+  const int bb = clampi(ds(200 * (fY - fZ) + 128 * 32768, 15), 0, 255);
+  // CLAHE bilinear LUT interpolation (A.2): fp32, every multiply and add rounded separately
+  const float p00 = (float)__ldg(lut1 + ctx1 + L), p01 = (float)__ldg(lut1 + ctx2 + L);
+  const float p10 = (float)__ldg(lut2 + ctx1 + L), p11 = (float)__ldg(lut2 + ctx2 + L);
+  const float top = __fadd_rn(__fmul_rn(p00, cxa1), __fmul_rn(p01, cxa));
+  const float bot = __fadd_rn(__fmul_rn(p10, cxa1), __fmul_rn(p11, cxa));
+  L = clampi(__float2int_rn(__fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya))), 0, 255);
+  // Lab -> RGB (A.3)
+  const int yy = T.lab_y[L], ify = T.lab_ify[L];
+  const int adiv = ((5 * a * 53687 + 128) >> 13) - 4194;
+  const int bdiv = ((bb * 41943 + 16) >> 9) - 10485 + 1;
+  const int X = ab2xz(ify + adiv), Z = ab2xz(ify - bdiv);
+  const int ro = clampi(ds(12615 * X - 6296 * yy - 2223 * Z, 14), 0, 4095);
+  const int go = clampi(ds(-3773 * X + 7684 * yy + 185 * Z, 14), 0, 4095);
+  const int bo = clampi(ds(217 * X - 836 * yy + 4715 * Z, 14), 0, 4095);
+  return (uint32_t)T.invgam[ro] | ((uint32_t)T.invgam[go] << 8) | ((uint32_t)T.invgam[bo] << 16);
+}
+
 // RAD = blur radius (compile time: the tap loops unroll and the halo geometry is constant).  Work split:
 // one warp per tile row, lanes over columns, so everything that depends only on the row (source row pointer,
 // CLAHE y-interpolation, LUT rows) or only on the column (reflected x, x-interpolation) is hoisted out of the
@@ -250,7 +281,8 @@ post_apply_kernel(ImgView img, OutView out, const WowsrTables* __restrict__ tabs
   SmemTabs& T = *reinterpret_cast<SmemTabs*>(smem_raw);
   constexpr int r = RAD;
   constexpr int EW = PB_TX + 2 * r, EH = PB_TY + 2 * r;
-  constexpr int NCOL = (EW + 31) / 32;  // columns of the halo tile per lane
+  constexpr int NFULL = EW / 32;          // full 32-lane column blocks of the halo tile
+  constexpr int TAILW = EW - 32 * NFULL;  // remaining columns (2r)
   constexpr int NWARP = PB_THREADS / 32;
   uint32_t* E = reinterpret_cast<uint32_t*>(smem_raw + ((sizeof(SmemTabs) + 15) & ~15));  // [EH][EW] packed rgb
   uint2* Hs = reinterpret_cast<uint2*>(E + EH * EW + ((EH * EW) & 1));                    // [EH][PB_TX] 3 x u16 (+pad)
@@ -265,13 +297,12 @@ post_apply_kernel(ImgView img, OutView out, const WowsrTables* __restrict__ tabs
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int bx = (tile % tiles_x) * PB_TX;
     const int by = row0 + (tile / tiles_x) * PB_TY;
-    // ---- per-column constants of this tile (registers) ----
-    int goff[NCOL], ctx1[NCOL], ctx2[NCOL];
-    float cxa[NCOL], cxa1[NCOL];
+    // ---- per-column constants of this tile (registers), full 32-lane column blocks only ----
+    int goff[NFULL], ctx1[NFULL], ctx2[NFULL];
+    float cxa[NFULL], cxa1[NFULL];
 #pragma unroll
-    for (int c = 0; c < NCOL; c++) {
-      const int ex = lane + 32 * c;
-      const int gx = reflect101(bx - r + (ex < EW ? ex : 0), img.W);
+    for (int c = 0; c < NFULL; c++) {
+      const int gx = reflect101(bx - r + lane + 32 * c, img.W);
       goff[c] = gx * 3;
       const float txf = __fsub_rn(__fmul_rn((float)gx, k.inv_tw), 0.5f);
       const int t1 = (int)floorf(txf);
@@ -287,8 +318,7 @@ post_apply_kernel(ImgView img, OutView out, const WowsrTables* __restrict__ tabs
       uint32_t* erow = E + ey * EW;
       if (gyb < 0 || gyb >= img.rows) {  // tile overhang beyond the band: never consumed
 #pragma unroll
-        for (int c = 0; c < NCOL; c++)
-          if (lane + 32 * c < EW) erow[lane + 32 * c] = 0;
+        for (int c = 0; c < NFULL; c++) erow[lane + 32 * c] = 0;
         continue;
       }
       const uint8_t* rp = img.data + (long long)gyb * img.pitch;
@@ -298,40 +328,30 @@ post_apply_kernel(ImgView img, OutView out, const WowsrTables* __restrict__ tabs
       const uint8_t* lut1 = luts + ((max(t1, 0) * k.grid) << 8);
       const uint8_t* lut2 = luts + ((min(t1 + 1, k.grid - 1) * k.grid) << 8);
 #pragma unroll
-      for (int c = 0; c < NCOL; c++) {
-        const int ex = lane + 32 * c;
-        if (ex >= EW) break;
-        const uint8_t* p = rp + goff[c];
-        const int cr = __ldg(p), cg = __ldg(p + 1), cb = __ldg(p + 2);
-        uint32_t e;
-        if (do_clahe) {
-          // RGB -> Lab (A.1)
-          const int R = T.gam[cr], G = T.gam[cg], B = T.gam[cb];
-          const int fX = T.cbrt[ds(1777 * R + 1541 * G + 778 * B, 12)];
-          const int fY = T.cbrt[ds(871 * R + 2929 * G + 296 * B, 12)];
-          const int fZ = T.cbrt[ds(73 * R + 448 * G + 3575 * B, 12)];
-          int L = clampi(ds(296 * fY - 1336934, 15), 0, 255);
-          const int a = clampi(ds(500 * (fX - fY) + 128 * 32768, 15), 0, 255);
-          const int bb = clampi(ds(200 * (fY - fZ) + 128 * 32768, 15), 0, 255);
-          // CLAHE bilinear LUT interpolation (A.2): fp32, every multiply and add rounded separately
-          const float p00 = (float)__ldg(lut1 + ctx1[c] + L), p01 = (float)__ldg(lut1 + ctx2[c] + L);
-          const float p10 = (float)__ldg(lut2 + ctx1[c] + L), p11 = (float)__ldg(lut2 + ctx2[c] + L);
-          const float top = __fadd_rn(__fmul_rn(p00, cxa1[c]), __fmul_rn(p01, cxa[c]));
-          const float bot = __fadd_rn(__fmul_rn(p10, cxa1[c]), __fmul_rn(p11, cxa[c]));
-          L = clampi(__float2int_rn(__fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya))), 0, 255);
-          // Lab -> RGB (A.3)
-          const int yy = T.lab_y[L], ify = T.lab_ify[L];
-          const int adiv = ((5 * a * 53687 + 128) >> 13) - 4194;
-          const int bdiv = ((bb * 41943 + 16) >> 9) - 10485 + 1;
-          const int X = ab2xz(ify + adiv), Z = ab2xz(ify - bdiv);
-          const int ro = clampi(ds(12615 * X - 6296 * yy - 2223 * Z, 14), 0, 4095);
-          const int go = clampi(ds(-3773 * X + 7684 * yy + 185 * Z, 14), 0, 4095);
-          const int bo = clampi(ds(217 * X - 836 * yy + 4715 * Z, 14), 0, 4095);
-          e = (uint32_t)T.invgam[ro] | ((uint32_t)T.invgam[go] << 8) | ((uint32_t)T.invgam[bo] << 16);
-        } else {
-          e = (uint32_t)cr | ((uint32_t)cg << 8) | ((uint32_t)cb << 16);
+      for (int c = 0; c < NFULL; c++)
+        erow[lane + 32 * c] = enhance_px(rp + goff[c], do_clahe, T, lut1, lut2, ctx1[c], ctx2[c], cxa[c], cxa1[c], ya, ya1);
+    }
+    // the 2r columns right of the full blocks, all rows, packed over the whole block (a third column block per row
+    // would run with 2r of 32 lanes)
+    if constexpr (TAILW > 0) {
+      for (int idx = tid; idx < EH * TAILW; idx += PB_THREADS) {
+        const int ey = idx / TAILW, ex = 32 * NFULL + (idx - ey * TAILW);
+        const int gy = reflect101(by - r + ey, img.H);
+        const int gyb = gy - img.y0;
+        uint32_t e = 0;
+        if (gyb >= 0 && gyb < img.rows) {
+          const int gx = reflect101(bx - r + ex, img.W);
+          const float txf = __fsub_rn(__fmul_rn((float)gx, k.inv_tw), 0.5f);
+          const int tx1 = (int)floorf(txf);
+          const float xa = __fsub_rn(txf, (float)tx1), xa1 = __fsub_rn(1.0f, xa);
+          const float tyf = __fsub_rn(__fmul_rn((float)gy, k.inv_th), 0.5f);
+          const int ty1 = (int)floorf(tyf);
+          const float ya = __fsub_rn(tyf, (float)ty1), ya1 = __fsub_rn(1.0f, ya);
+          e = enhance_px(img.data + (long long)gyb * img.pitch + gx * 3, do_clahe, T, luts + ((max(ty1, 0) * k.grid) << 8),
+                         luts + ((min(ty1 + 1, k.grid - 1) * k.grid) << 8), max(tx1, 0) << 8, min(tx1 + 1, k.grid - 1) << 8, xa,
+                         xa1, ya, ya1);
         }
-        erow[ex] = e;
+        E[ey * EW + ex] = e;
       }
     }
     __syncthreads();
@@ -342,16 +362,16 @@ post_apply_kernel(ImgView img, OutView out, const WowsrTables* __restrict__ tabs
         for (int c = 0; c < PB_TX / 32; c++) {
           const int x = lane + 32 * c;
           const uint32_t* e = E + ey * EW + x;
-          uint32_t ar = 0, ag = 0, ab = 0;
+          // R and G share one multiply-add: sum(taps) = 256, so each 16-bit half stays below 65536 and never carries
+          uint32_t arg = 0, ab = 0;
 #pragma unroll
           for (int t = 0; t <= 2 * r; t++) {
             const uint32_t px = e[t];
             const uint32_t w = k.taps[t];
-            ar += w * (px & 255);
-            ag += w * ((px >> 8) & 255);
-            ab += w * ((px >> 16) & 255);
+            arg += w * __byte_perm(px, 0u, 0x4140);  // r | g << 16
+            ab += w * __byte_perm(px, 0u, 0x4442);   // b
           }
-          Hs[ey * PB_TX + x] = make_uint2(ar | (ag << 16), ab);
+          Hs[ey * PB_TX + x] = make_uint2(arg, ab);
         }
       }
       __syncthreads();
@@ -373,10 +393,10 @@ post_apply_kernel(ImgView img, OutView out, const WowsrTables* __restrict__ tabs
 #pragma unroll
           for (int t = 0; t <= 2 * r; t++) {
             const uint2 hv = Hs[(y + t) * PB_TX + x];
-            const uint32_t w = k.taps[t];
-            ar += w * (hv.x & 0xFFFF);
-            ag += w * (hv.x >> 16);
-            ab += w * (hv.y & 0xFFFF);
+            const uint32_t w = k.taps[t];  // < 256: a two-way dot product with one zero weight picks a 16-bit half
+            ar = __dp2a_lo(hv.x, w, ar);
+            ag = __dp2a_lo(hv.x, w << 8, ag);
+            ab = __dp2a_lo(hv.y, w, ab);
           }
           const int br = (ar + 32768) >> 16, bg = (ag + 32768) >> 16, bb = (ab + 32768) >> 16;
           cr = clampi(__float2int_rn(__fadd_rn(__fmul_rn((float)cr, k.alpha), __fmul_rn((float)br, k.beta))), 0, 255);
