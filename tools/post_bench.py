@@ -6,7 +6,7 @@ import numpy as np, torch
 import wowsr_b200 as ws
 from tests.conftest import image_like
 h = ws.Handle(0)
-h.set_option('hist_match', int(sys.argv[1]) if len(sys.argv) > 1 else 1)
+h.set_option('hist_match', int(sys.argv[1]) if len(sys.argv) > 1 else 0)   # 0 = production path (plain per-lane shared atomics)
 for size in (4096, 16384):
     base = image_like(1024, 1024, seed=3)
     img = torch.from_numpy(base).cuda().repeat(size // 1024, size // 1024, 1).contiguous()
