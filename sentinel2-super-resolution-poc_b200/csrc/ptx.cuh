@@ -5,8 +5,9 @@
 #include <cuda.h>
 #include <stdint.h>
 
-// Compile-time experiment switches for the MMA issuer (tools/ab_bench.sh): bit 0 = single-lane issue loop,
-// bit 1 = spinning test_wait in the issuer's hot waits.
+// Compile-time experiment switches (tools/build_variant.sh, tools/experiments/README.md): bit 0 = single-lane MMA issue loop,
+// bit 1 = spinning test_wait in the issuer hot waits, bit 2 = epilogue clock64 instrumentation, bit 3 = L2 prefetch of the
+// fp32 residual.  The product build is WOWSR_VAR = 0.
 #ifndef WOWSR_VAR
 #define WOWSR_VAR 0
 #endif
