@@ -9,6 +9,7 @@
 
 #include "common.h"
 #include "conv_kernels.cuh"
+#include "trunk_kernel.cuh"
 
 namespace {
 
@@ -39,6 +40,7 @@ struct ConvNet {
   float* first_b = nullptr;
   std::vector<LayerW> layers;
   DevBuf dense0, dense1, feat, trunk, rrdb, lo, up1, hra, hrb, wins, winxy, err;
+  DevBuf trunk_tab, trunk_ctr;  // experimental dataflow trunk (trunk_kernel.cuh): weight table, dependency counters
 };
 
 void wowsr_net_free(ConvNet* n) {
@@ -53,7 +55,7 @@ void wowsr_net_free(ConvNet* n) {
   }
   if (n->first_w) cudaFree(n->first_w);
   if (n->first_b) cudaFree(n->first_b);
-  DevBuf* bufs[] = {&n->dense0, &n->dense1, &n->feat, &n->trunk, &n->rrdb, &n->lo, &n->up1, &n->hra, &n->hrb, &n->wins, &n->winxy, &n->err};
+  DevBuf* bufs[] = {&n->trunk_tab, &n->trunk_ctr, &n->dense0, &n->dense1, &n->feat, &n->trunk, &n->rrdb, &n->lo, &n->up1, &n->hra, &n->hrb, &n->wins, &n->winxy, &n->err};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   delete n;
@@ -123,7 +125,8 @@ int upload_layer(wowsr_ctx* ctx, LayerW& L, const float* w, const float* b, int 
   // double buffer (run_conv picks the mode with the same test)
   // Measured (profiles/r01_epilogue_breakdown.txt, exp9): -4 % cycles per rdb.conv5 tile but no time gain under the
   // power cap, so the mode is opt-in (option tc_chunk32=1 before loading the network).
-  if (wowsr_opt(ctx, "tc_chunk32", 0) && L.chunk_bytes * L.n_chunks + 2 * (size_t)TC_ASTAGE + SMEM_SLACK > SMEM_LIMIT) {
+  if ((wowsr_opt(ctx, "tc_chunk32", 0) && L.chunk_bytes * L.n_chunks + 2 * (size_t)TC_ASTAGE + SMEM_SLACK > SMEM_LIMIT) ||
+      wowsr_opt(ctx, "trunk_dataflow", 0)) {  // the experimental dataflow trunk streams every layer in 32-channel chunks
     L.chunk_bytes32 = (size_t)3 * 3 * N * 64;
     const int nc32 = cin / 32;
     std::vector<uint8_t> p32(L.chunk_bytes32 * nc32, 0), p32v(L.chunk_bytes32 * nc32, 0);
@@ -404,6 +407,66 @@ int check_err_flag(wowsr_ctx* ctx, ConvNet* net, cudaStream_t st) {
   return 0;
 }
 
+// EXPERIMENTAL (option trunk_dataflow=1, see trunk_kernel.cuh): the residual trunk of one batch as one persistent launch
+// per group of `trunk_group` windows.  Expects conv_first's outputs in dense0 / rrdb; leaves the trunk output where the
+// layer-by-layer loop would (hi in dense[(3 * num_block) & 1], fp32 in rrdb).
+int run_trunk_dataflow(wowsr_ctx* ctx, ConvNet* net, int nb, int h, int w, const F32Layout& fl, bool body16, bool tail16,
+                       cudaStream_t st) {
+  const int n_rdb = 3 * net->num_block;
+  for (int i = 0; i < n_rdb * 5; i++)
+    if (!net->layers[i].wpack32) return wowsr_fail(ctx, WOWSR_ERR_STATE, "set option trunk_dataflow=1 before loading the network");
+  if (!net->trunk_tab.p) {
+    std::vector<TrunkLayerW> tab(n_rdb * 5);
+    for (int i = 0; i < n_rdb * 5; i++) tab[i] = TrunkLayerW{net->layers[i].wpack32, net->layers[i].wpack32_v, net->layers[i].bias};
+    if (int e = wowsr_ensure(ctx, net->trunk_tab, tab.size() * sizeof(TrunkLayerW))) return e;
+    WCUDA(ctx, cudaMemcpy(net->trunk_tab.p, tab.data(), tab.size() * sizeof(TrunkLayerW), cudaMemcpyHostToDevice));
+  }
+  int G = (int)wowsr_opt(ctx, "trunk_group", 2);
+  if (G < 1) G = 1;
+  if (int e = wowsr_ensure(ctx, net->trunk_ctr, (size_t)n_rdb * 5 * G * 4)) return e;
+  TrunkParams T;
+  memset(&T, 0, sizeof T);
+  T.h = h; T.w = w; T.n_rdb = n_rdb;
+  T.fp16 = body16; T.last_fp16 = tail16;
+  T.idesc_base = make_idesc_f16(128, 0, body16);
+  T.f32 = fl;
+  T.strip_x0 = fl.x0;  // strip columns (blocked along y in the fp32 / lo buffers) are covered by vertical tiles
+  for (int kind = 0; kind < 2; kind++) {
+    const int R = kind ? 4 : 8;
+    TrunkKind& K = T.kind[kind];
+    K.tiles_x = (T.strip_x0 + TC_RUN - 1) / TC_RUN;
+    K.tiles_y = (h + R - 1) / R;
+    K.n_h = K.tiles_x * K.tiles_y;
+    K.v_runs = fl.rem ? (h + TC_RUN - 1) / TC_RUN : 0;
+    K.v_rows = fl.rem ? (fl.rem + R - 1) / R : 0;
+    K.n_v = K.v_runs * K.v_rows;
+    K.n = K.n_h + K.n_v;
+  }
+  T.dense[0] = (uint16_t*)net->dense0.p; T.dense[1] = (uint16_t*)net->dense1.p;
+  T.lo = (uint16_t*)net->lo.p; T.rrdb = (float*)net->rrdb.p;
+  T.layers = (const TrunkLayerW*)net->trunk_tab.p;
+  T.counters = (unsigned int*)net->trunk_ctr.p;
+  T.err_flag = (int*)net->err.p;
+  T.n_stage = (int)((SMEM_LIMIT - SMEM_SLACK - 2 * (size_t)TRUNK_WBUF_BYTES - 8192) / TC_ASTAGE32);
+  if (T.n_stage > TC_MAX_STAGES) T.n_stage = TC_MAX_STAGES;
+  const size_t smem = (size_t)T.n_stage * TC_ASTAGE32 + 2 * (size_t)TRUNK_WBUF_BYTES + 8192 + SMEM_SLACK;
+  CUtensorMap tm[2][2];
+  for (int b = 0; b < 2; b++)
+    for (int v = 0; v < 2; v++)
+      if (int e = make_tmap(ctx, &tm[b][v], b ? net->dense1.p : net->dense0.p, 192, w, h, nb, body16, v == 1, true)) return e;
+  WCUDA(ctx, cudaFuncSetAttribute(rdb_trunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+  for (int g0 = 0; g0 < nb; g0 += G) {
+    T.win0 = g0;
+    T.G = std::min(G, nb - g0);
+    const long long n_tasks = (long long)n_rdb * T.G * (4 * T.kind[0].n + T.kind[1].n);
+    const int grid = (int)std::min<long long>(ctx->sm_count, n_tasks);  // every CTA must be resident: tasks wait on each other
+    WCUDA(ctx, cudaMemsetAsync(net->trunk_ctr.p, 0, (size_t)n_rdb * 5 * G * 4, st));
+    rdb_trunk_kernel<<<grid, TC_THREADS, smem, st>>>(tm[0][0], tm[0][1], tm[1][0], tm[1][1], T);
+    WLAUNCH_CHECK(ctx);
+  }
+  return 0;
+}
+
 // One batch of equally sized windows through the whole RRDBNet.
 int rrdbnet_batch(wowsr_ctx* ctx, ConvNet* net, const uint8_t* img, long long pitch, const wowsr_window* wins, int nb,
                   uint8_t* out, long long out_pitch, float* out_f32, long long out_f32_pitch, cudaStream_t st) {
@@ -467,7 +530,13 @@ int rrdbnet_batch(wowsr_ctx* ctx, ConvNet* net, const uint8_t* img, long long pi
   void* cur = net->dense0.p;
   void* nxt = net->dense1.p;
   size_t li = 0;
-  for (int b = 0; b < net->num_block; b++)
+  const bool dataflow = hilo && wowsr_opt(ctx, "trunk_dataflow", 0) && wowsr_opt(ctx, "conv_impl", 0) == 0;
+  if (dataflow) {
+    if (int e = run_trunk_dataflow(ctx, net, nb, h, w, fl, body16, tail16, st)) return e;
+    li = (size_t)net->num_block * 15;
+    if ((net->num_block * 3) & 1) std::swap(cur, nxt);
+  }
+  for (int b = 0; b < (dataflow ? 0 : net->num_block); b++)
     for (int r = 0; r < 3; r++) {
       for (int k = 0; k < 4; k++) {
         LayerIO io;

@@ -497,7 +497,10 @@ __device__ __forceinline__ void epi_plain32(const EpiConst& E, float (&v)[32], c
   epi_store16_quad(v, E.out_fp16, px, step, u, u_lim);
 }
 
-// `fb` / `lb` = element index of channel ch0 of this lane's pixel in the warp-blocked fp32 / 16-bit buffers
+// `fb` / `lb` = element index of channel ch0 of this lane's pixel in the warp-blocked fp32 / 16-bit buffers.
+// CG: read the residuals with ld.global.cg (L2 only) — needed when other SMs wrote them earlier in the SAME launch
+// (trunk_kernel.cuh); across launches the default path is fine because L1 is invalidated at launch boundaries.
+template <bool CG = false>
 __device__ __forceinline__ void epi_res32(const EpiConst& E, float (&v)[32], const float* __restrict__ bias, long long fb, long long lb,
                                           bool valid, uint16_t* px, long long step, int u, int u_lim) {
   float t[32];
@@ -505,7 +508,7 @@ __device__ __forceinline__ void epi_res32(const EpiConst& E, float (&v)[32], con
     const uint4* r = reinterpret_cast<const uint4*>(E.lo_in + lb);
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      const uint4 w = valid ? r[i * 32] : make_uint4(0u, 0u, 0u, 0u);
+      const uint4 w = valid ? (CG ? __ldcg(r + i * 32) : r[i * 32]) : make_uint4(0u, 0u, 0u, 0u);
       t[8 * i + 0] = __uint_as_float(w.x << 16); t[8 * i + 1] = __uint_as_float(w.x & 0xFFFF0000u);
       t[8 * i + 2] = __uint_as_float(w.y << 16); t[8 * i + 3] = __uint_as_float(w.y & 0xFFFF0000u);
       t[8 * i + 4] = __uint_as_float(w.z << 16); t[8 * i + 5] = __uint_as_float(w.z & 0xFFFF0000u);
@@ -515,7 +518,7 @@ __device__ __forceinline__ void epi_res32(const EpiConst& E, float (&v)[32], con
     const float4* r = reinterpret_cast<const float4*>(E.res1 + fb);
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-      const float4 w = valid ? r[i * 32] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 w = valid ? (CG ? __ldcg(r + i * 32) : r[i * 32]) : make_float4(0.f, 0.f, 0.f, 0.f);
       t[4 * i] = w.x; t[4 * i + 1] = w.y; t[4 * i + 2] = w.z; t[4 * i + 3] = w.w;
     }
   }
@@ -526,7 +529,7 @@ __device__ __forceinline__ void epi_res32(const EpiConst& E, float (&v)[32], con
     const float4* r = reinterpret_cast<const float4*>(E.res2 + fb);
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-      const float4 w = valid ? r[i * 32] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 w = valid ? (CG ? __ldcg(r + i * 32) : r[i * 32]) : make_float4(0.f, 0.f, 0.f, 0.f);
       t[4 * i] = w.x; t[4 * i + 1] = w.y; t[4 * i + 2] = w.z; t[4 * i + 3] = w.w;
     }
 #pragma unroll

@@ -254,3 +254,29 @@ def test_kernel_option_paths_agree(ws):
     assert np.abs(f - f_s).max() < tol
     u8_c, f_c = run(tc_chunk32=1)      # rdb.conv5 streamed in 32-channel chunks (other K order, identity K-step per half)
     assert np.abs(f - f_c).max() < tol and np.abs(f_c - ref_f).max() < 4 * tol
+
+
+@pytest.mark.skipif(os.environ.get("WOWSR_TEST_DATAFLOW") != "1",
+                    reason="experimental dataflow trunk (csrc/trunk_kernel.cuh): round-2 work in progress, opt-in")
+def test_experimental_dataflow_trunk_matches_layer_by_layer(ws):
+    """The persistent L2-resident trunk must reproduce the layer-by-layer path: same kernels' arithmetic per tile, so
+    float outputs agree to the operand-rounding noise floor and uint8 within 1 LSB."""
+    blocks = 2
+    sd = R.calibrate_conv_last(R.random_init_state_dict(4, blocks), blocks)
+    img = np.random.default_rng(13).integers(0, 256, (560, 290, 3), dtype=np.uint8)   # 3 x 2 windows of 276 wide: strips
+
+    def run(**opts):
+        h = ws.Handle(0)
+        for k, v in opts.items():
+            h.set_option(k, v)
+        h.load_rrdbnet(_tensors(sd, blocks), blocks, precision="bf16")
+        out = h.enhance_host(img, 256, want_float=True)
+        h.close()
+        return out
+
+    u8, f = run()
+    u8_d, f_d = run(trunk_dataflow=1)
+    ref_f = R.enhance_float(sd, img, blocks, 256)
+    tol = 0.005 * max(1.0, np.abs(ref_f).max())
+    assert np.abs(f - f_d).max() < tol and np.abs(f_d - ref_f).max() < 4 * tol
+    assert (np.abs(u8.astype(int) - u8_d.astype(int)) <= 1).mean() >= 0.999
