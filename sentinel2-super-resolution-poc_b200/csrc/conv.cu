@@ -463,6 +463,15 @@ int run_trunk_dataflow(wowsr_ctx* ctx, ConvNet* net, int nb, int h, int w, const
     WCUDA(ctx, cudaMemsetAsync(net->trunk_ctr.p, 0, (size_t)n_rdb * 5 * G * 4, st));
     rdb_trunk_kernel<<<grid, TC_THREADS, smem, st>>>(tm[0][0], tm[0][1], tm[1][0], tm[1][1], T);
     WLAUNCH_CHECK(ctx);
+    if (wowsr_opt(ctx, "trunk_debug", 0)) {  // bring-up aid: published-warp counters per (rdb, layer, window) after the launch
+      std::vector<unsigned int> c((size_t)n_rdb * 5 * G);
+      cudaError_t ce = cudaStreamSynchronize(st);
+      cudaMemcpy(c.data(), net->trunk_ctr.p, c.size() * 4, cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[trunk_debug] group %d: sync=%s grid=%d tasks=%lld n0=%d n1=%d targets %d / %d; counters:", g0,
+              cudaGetErrorString(ce), grid, n_tasks, T.kind[0].n, T.kind[1].n, T.kind[0].n * TC_EPI_WARPS, T.kind[1].n * TC_EPI_WARPS);
+      for (size_t i = 0; i < c.size() && i < 40; i++) fprintf(stderr, " %u", c[i]);
+      fprintf(stderr, "\n");
+    }
   }
   return 0;
 }

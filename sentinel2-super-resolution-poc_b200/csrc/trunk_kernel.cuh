@@ -1,5 +1,8 @@
-// EXPERIMENTAL — round-2 work in progress.  NOT on the product path (option trunk_dataflow=1 selects it), NOT yet
-// validated on hardware: it compiles for sm_100a and is kept here so the next round starts from code, not from a plan.
+// EXPERIMENTAL — round-2 work in progress.  NOT on the product path (option trunk_dataflow=1, set before loading the
+// network, selects it).  First hardware runs (profiles/r01_dataflow_trunk_trial.txt): output equal to the layer-by-layer
+// path within the operand-rounding noise floor (uint8 within 1 LSB on 100 % of pixels; 1 / 9 / 25 windows), no speed-up
+// yet: 25 windows of 276 x 276, 23 blocks: 72 ms layer-by-layer, 90 ms with groups of 2, 74-78 ms with groups of 4 —
+// window-level dependencies leave bubbles at 2 windows per group, and 4 windows no longer fit the L2.
 //
 // rdb_trunk_kernel — the whole residual trunk (num_block x 3 RDBs x 5 convs, cnn_super_resolution.py:85-107) of a small
 // GROUP of windows in ONE persistent launch, so that the RDB dense buffer of the group (2 windows of 276 x 276: 58 MB)
@@ -203,13 +206,16 @@ rdb_trunk_kernel(const __grid_constant__ CUtensorMap tm_h0, const __grid_constan
     const uint32_t full0 = ptx::smem_u32(&ctl->a_full[0]), empty0 = ptx::smem_u32(&ctl->a_empty[0]);
     IssueState S{0, 0u, 1u << 18};
     uint32_t wcount = 0;
-    if (n_my > 0 && !ptx::mbar_wait_hot(full0, 0, S.wd)) tc_fail(Pm, 23);
     for (int i = 0; i < n_my; i++) {
       const TrunkTask t = trunk_decode(T, task0 + i * task_step);
       const int n_chunks = (64 + 32 * t.k) / 32;
       const int accbuf = i & 1;
       const uint32_t acc_phase = (i >> 1) & 1;
       if (!ptx::mbar_wait_hot(ptx::smem_u32(&ctl->t_empty[accbuf]), acc_phase ^ 1, S.wd)) tc_fail(Pm, 21);
+      // The first stage of a task is waited for HERE, not prefetch-waited inside the previous task's last stage: the
+      // next task's loads are gated by its dependencies, which may include this CTA's previous task — whose completion
+      // must therefore never wait on them.
+      if (!ptx::mbar_wait_hot(full0 + 8 * S.stage, S.aphase, S.wd)) tc_fail(Pm, 23);
       ptx::tc_fence_after();
       const uint32_t acc_base = tmem_base + accbuf * 256;  // R * N = 256 columns for both layer kinds
       const bool ident_layer = t.k == 4 && (t.rdb % 3) != 0;  // rdb2 / rdb3 of an RRDB take the trunk's hi half through the MMA
@@ -219,7 +225,7 @@ rdb_trunk_kernel(const __grid_constant__ CUtensorMap tm_h0, const __grid_constan
         wcount++;
         ptx::tc_fence_after();
         const uint64_t bd = bdesc64 + (uint64_t)((wb * TRUNK_WBUF_BYTES) >> 4);
-        const bool last_chunk = (c == n_chunks - 1) && (i == n_my - 1);
+        const bool last_chunk = c == n_chunks - 1;  // no prefetch-wait across a task boundary (see above)
         const uint64_t idd = id_desc64 + (uint64_t)((c & 1) * (4096 >> 4));
         if (t.k < 4) {
           if (c == 0) issue_chunk<32, 8, true, true, false, false>(Pm, S, elected, elected, last_chunk, full0, empty0, adesc64, bd, acc_base, T.idesc_base);
