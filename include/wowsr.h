@@ -124,6 +124,22 @@ int64_t wowsr_get_table(int32_t id, void* out, int64_t cap);
 /* 8-bit fixed-point Gaussian taps cv2 derives for sigma (ksize=(0,0)); returns ksize. */
 int32_t wowsr_gaussian_taps(double sigma, int32_t* taps, int32_t cap);
 
+/* HSV vegetation mask — compute_green_mask_hsv (server/app/vector_extraction.py:222-270):
+ * cv2.cvtColor(rgb, COLOR_RGB2HSV) (H in [0,180)), cv2.inRange per colour range (bounds inclusive),
+ * bitwise_or of the range masks, (> 0).astype(float32).  The reference uses two ranges: green
+ * [hue_min..hue_max, sat_min..255, val_min..255] (:255-259) and brown [10..35, 20..200, 40..200]
+ * (:262-264).  `rgb` is a device band (rows are band-relative in `mask_dev`, a float32 [rows][W]
+ * array with `mask_pitch` BYTES between rows); 1 <= n_ranges <= 4. */
+typedef struct wowsr_hsv_range {
+  uint8_t lo[3];   /* lower (H, S, V), inclusive */
+  uint8_t hi[3];   /* upper (H, S, V), inclusive */
+} wowsr_hsv_range;
+int wowsr_green_mask(wowsr_ctx* ctx, const wowsr_image* rgb, const wowsr_hsv_range* ranges,
+                     int32_t n_ranges, float* mask_dev, int64_t mask_pitch, void* stream);
+/* Same with HOST buffers (H2D, kernel, D2H, synchronous): rgb [H,W,3] uint8 -> mask [H,W] float32. */
+int wowsr_green_mask_host(wowsr_ctx* ctx, const uint8_t* rgb_host, int32_t H, int32_t W,
+                          const wowsr_hsv_range* ranges, int32_t n_ranges, float* mask_host);
+
 /* ------------------------------------------------------------------------------------------ */
 /* window planner: RealESRGAN._tile_process geometry (cnn_super_resolution.py:244-278)         */
 /* ------------------------------------------------------------------------------------------ */

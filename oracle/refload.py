@@ -47,6 +47,42 @@ def load():
     return cnn, wow, farm
 
 
+def load_vector_extraction(read_bands):
+    """The unmodified ``app.vector_extraction`` with ``rasterio.open(path)`` served by ``read_bands(path) -> [band arrays]``
+    (rasterio and its mask / features / warp submodules are not installed; only ``open(...).read(i)`` is exercised by
+    compute_green_mask_hsv, vector_extraction.py:237-243)."""
+    if not available():
+        raise RuntimeError("reference tree not present")
+    _stub_rasterio()
+    r = sys.modules["rasterio"]
+    for name, attrs in (("mask", ("mask",)), ("features", ("shapes",)), ("warp", ("calculate_default_transform", "reproject", "Resampling"))):
+        m = types.ModuleType("rasterio." + name)
+        for a in attrs:
+            setattr(m, a, object)
+        setattr(r, name, m)
+        sys.modules["rasterio." + name] = m
+
+    class _Dataset:
+        def __init__(self, path):
+            self.bands = read_bands(path)
+            self.count = len(self.bands)
+
+        def read(self, i):
+            return self.bands[i - 1]
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+    r.open = _Dataset
+    if REF_SERVER not in sys.path:
+        sys.path.insert(0, REF_SERVER)
+    import importlib
+    return importlib.import_module("app.vector_extraction")
+
+
 def make_upsampler(cnn, model, tile_size=256, scale=4):
     """A reference RealESRGAN wrapper around ``model`` without running its network-bound __init__."""
     import torch

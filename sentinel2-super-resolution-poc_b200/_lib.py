@@ -30,6 +30,10 @@ class Window(C.Structure):
                 ("ox0", C.c_int32), ("oy0", C.c_int32), ("ox1", C.c_int32), ("oy1", C.c_int32)]
 
 
+class HsvRange(C.Structure):
+    _fields_ = [("lo", C.c_uint8 * 3), ("hi", C.c_uint8 * 3)]
+
+
 STAGE_CLAHE, STAGE_UNSHARP, STAGE_VEG, STAGE_ALL = 1, 2, 4, 7
 
 _lib = None
@@ -51,6 +55,8 @@ _SIGS = {
                                    C.POINTER(Image), C.c_void_p]),
     "wowsr_post_process_dev": (C.c_int, [C.c_void_p, C.POINTER(Image), C.POINTER(PostParams), C.POINTER(Image), C.c_void_p]),
     "wowsr_post_process_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(PostParams), C.c_void_p]),
+    "wowsr_green_mask": (C.c_int, [C.c_void_p, C.POINTER(Image), C.POINTER(HsvRange), C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
+    "wowsr_green_mask_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(HsvRange), C.c_int32, C.c_void_p]),
     "wowsr_clahe_geometry": (None, [C.c_int32, C.c_int32, C.c_int32] + [C.POINTER(C.c_int32)] * 4),
     "wowsr_get_table": (C.c_int64, [C.c_int32, C.c_void_p, C.c_int64]),
     "wowsr_gaussian_taps": (C.c_int32, [C.c_double, C.POINTER(C.c_int32), C.c_int32]),
@@ -170,6 +176,33 @@ class Handle:
     def post_apply(self, src: Image, luts_ptr, params, row0, row1, dst: Image, stream=0):
         self._check(self._L.wowsr_post_apply(self._h, C.byref(src), C.c_void_p(luts_ptr), C.byref(params), row0, row1, C.byref(dst),
                                              C.c_void_p(stream)), "post_apply")
+
+    @staticmethod
+    def _hsv_ranges(ranges):
+        """[((h0, s0, v0), (h1, s1, v1)), ...] -> ctypes array; bounds are inclusive like cv2.inRange."""
+        arr = (HsvRange * len(ranges))()
+        for a, (lo, hi) in zip(arr, ranges):
+            for c in range(3):
+                if not (0 <= int(lo[c]) <= 255 and 0 <= int(hi[c]) <= 255):
+                    raise ValueError("HSV bounds must fit uint8")
+                a.lo[c], a.hi[c] = int(lo[c]), int(hi[c])
+        return arr
+
+    def green_mask_host(self, img: np.ndarray, ranges) -> np.ndarray:
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        if img.ndim != 3 or img.shape[2] != 3:
+            raise ValueError("expected HxWx3 uint8")
+        out = np.empty(img.shape[:2], dtype=np.float32)
+        arr = self._hsv_ranges(ranges)
+        self._check(self._L.wowsr_green_mask_host(self._h, img.ctypes.data, img.shape[0], img.shape[1], arr, len(arr),
+                                                  out.ctypes.data), "green_mask_host")
+        return out
+
+    def green_mask_dev(self, src_ptr, H, W, ranges, mask_ptr, stream=0, pitch=None, mask_pitch=None):
+        a = Image(src_ptr, pitch or W * 3, W, H, 0, H)
+        arr = self._hsv_ranges(ranges)
+        self._check(self._L.wowsr_green_mask(self._h, C.byref(a), arr, len(arr), C.c_void_p(mask_ptr), mask_pitch or W * 4,
+                                             C.c_void_p(stream)), "green_mask")
 
     # -- network ------------------------------------------------------------------------------
     def load_rrdbnet(self, tensors, num_block, num_feat=64, num_grow=32, precision="bf16"):

@@ -415,6 +415,69 @@ post_apply_kernel(ImgView img, OutView out, const WowsrTables* __restrict__ tabs
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// HSV vegetation mask: vector_extraction.compute_green_mask_hsv (server/app/vector_extraction.py:251-270)
+// = cv2.cvtColor(RGB2HSV) -> cv2.inRange per colour range -> bitwise_or -> (> 0).astype(float32).
+// HBM-bound: 3 B read + 4 B written per pixel; a thread converts 4 pixels (three 32-bit loads, one float4 store).
+// The RGB -> HSV arithmetic is the one of vegetation_pixel above (App. A.6).
+// ---------------------------------------------------------------------------------------------
+
+constexpr int GM_THREADS = 256, GM_MAX_RANGES = 4;
+
+struct MaskK {
+  int n;
+  int lo[GM_MAX_RANGES][3], hi[GM_MAX_RANGES][3];  // inclusive bounds on (H, S, V), like cv2.inRange
+};
+
+__device__ __forceinline__ float hsv_in_ranges(int r, int g, int b, const MaskK& k, const uint32_t* sdiv, const uint32_t* hdiv) {
+  const int v = max(max(r, g), b), mn = min(min(r, g), b);
+  const int diff = v - mn;
+  const int s = (int)((diff * sdiv[v] + 2048u) >> 12);
+  int h;
+  if (v == r) h = g - b;
+  else if (v == g) h = b - r + 2 * diff;
+  else h = r - g + 4 * diff;
+  h = (h * (int)hdiv[diff] + 2048) >> 12;
+  if (h < 0) h += 180;
+  bool in = false;
+  for (int i = 0; i < k.n; i++)
+    in |= h >= k.lo[i][0] && h <= k.hi[i][0] && s >= k.lo[i][1] && s <= k.hi[i][1] && v >= k.lo[i][2] && v <= k.hi[i][2];
+  return in ? 1.0f : 0.0f;
+}
+
+__global__ void __launch_bounds__(GM_THREADS)
+green_mask_kernel(ImgView img, const WowsrTables* __restrict__ tabs, MaskK k, int vec_ok, float* __restrict__ mask,
+                  long long mask_pitch /* floats */) {
+  __shared__ uint32_t s_sdiv[256], s_hdiv[256];
+  for (int i = threadIdx.x; i < 256; i += GM_THREADS) {
+    s_sdiv[i] = tabs->sdiv[i];
+    s_hdiv[i] = tabs->hdiv[i];
+  }
+  __syncthreads();
+  const int gpr = (img.W + 3) >> 2;  // 4-pixel groups per row
+  const long long total = (long long)img.rows * gpr;
+  for (long long it = (long long)blockIdx.x * GM_THREADS + threadIdx.x; it < total; it += (long long)gridDim.x * GM_THREADS) {
+    const int row = (int)(it / gpr), x0 = (int)(it % gpr) * 4;
+    const uint8_t* rp = img.data + (long long)row * img.pitch;
+    float* mp = mask + (long long)row * mask_pitch + x0;
+    if (vec_ok && x0 + 3 < img.W) {
+      const uint32_t* q = reinterpret_cast<const uint32_t*>(rp + x0 * 3);
+      const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+      float4 o;
+      o.x = hsv_in_ranges(w0 & 255, (w0 >> 8) & 255, (w0 >> 16) & 255, k, s_sdiv, s_hdiv);
+      o.y = hsv_in_ranges(w0 >> 24, w1 & 255, (w1 >> 8) & 255, k, s_sdiv, s_hdiv);
+      o.z = hsv_in_ranges((w1 >> 16) & 255, w1 >> 24, w2 & 255, k, s_sdiv, s_hdiv);
+      o.w = hsv_in_ranges((w2 >> 8) & 255, (w2 >> 16) & 255, w2 >> 24, k, s_sdiv, s_hdiv);
+      *reinterpret_cast<float4*>(mp) = o;
+    } else {
+      for (int j = 0; j < 4 && x0 + j < img.W; j++) {
+        const uint8_t* p = rp + (x0 + j) * 3;
+        mp[j] = hsv_in_ranges(__ldg(p), __ldg(p + 1), __ldg(p + 2), k, s_sdiv, s_hdiv);
+      }
+    }
+  }
+}
+
 size_t post_smem_bytes(int r) {
   int EW = PB_TX + 2 * r, EH = PB_TY + 2 * r;
   size_t s = (sizeof(SmemTabs) + 15) & ~(size_t)15;
@@ -593,6 +656,46 @@ extern "C" int wowsr_post_process_host(wowsr_ctx* ctx, const uint8_t* rgb_host, 
   wowsr_image out{ctx->post_out.p, (int64_t)pitch, W, H, 0, H};
   if (int e = wowsr_post_process_dev(ctx, &in, p, &out, nullptr)) return e;
   WCUDA(ctx, cudaMemcpy2DAsync(out_host, (size_t)W * 3, ctx->post_out.p, pitch, (size_t)W * 3, H, cudaMemcpyDeviceToHost, 0));
+  WCUDA(ctx, cudaStreamSynchronize(0));
+  return WOWSR_OK;
+}
+
+extern "C" int wowsr_green_mask(wowsr_ctx* ctx, const wowsr_image* rgb, const wowsr_hsv_range* ranges, int32_t n_ranges,
+                                float* mask_dev, int64_t mask_pitch, void* stream) {
+  if (!ctx || !ranges || !mask_dev) return WOWSR_ERR_ARG;
+  if (int e = check_image(ctx, rgb, "input")) return e;
+  if (n_ranges < 1 || n_ranges > GM_MAX_RANGES) return wowsr_fail(ctx, WOWSR_ERR_ARG, "1..%d colour ranges", GM_MAX_RANGES);
+  if (mask_pitch < (int64_t)rgb->W * 4 || mask_pitch % 4) return wowsr_fail(ctx, WOWSR_ERR_ARG, "bad mask pitch");
+  DeviceGuard g(ctx->device);
+  MaskK k;
+  k.n = n_ranges;
+  for (int i = 0; i < n_ranges; i++)
+    for (int c = 0; c < 3; c++) {
+      k.lo[i][c] = ranges[i].lo[c];
+      k.hi[i][c] = ranges[i].hi[c];
+    }
+  ImgView v{(const uint8_t*)rgb->data, rgb->pitch, rgb->W, rgb->H, rgb->y0, rgb->rows};
+  const int vec_ok = rgb->pitch % 4 == 0 && ((uintptr_t)rgb->data) % 4 == 0 && mask_pitch % 16 == 0 && ((uintptr_t)mask_dev) % 16 == 0;
+  const long long groups = (long long)rgb->rows * ((rgb->W + 3) / 4);
+  long long blocks = (groups + GM_THREADS - 1) / GM_THREADS;
+  const long long cap = (long long)ctx->sm_count * (2048 / GM_THREADS);  // one resident wave, grid-stride beyond it
+  if (blocks > cap) blocks = cap;
+  green_mask_kernel<<<(unsigned)blocks, GM_THREADS, 0, (cudaStream_t)stream>>>(v, ctx->d_tables, k, vec_ok, mask_dev, mask_pitch / 4);
+  WLAUNCH_CHECK(ctx);
+  return WOWSR_OK;
+}
+
+extern "C" int wowsr_green_mask_host(wowsr_ctx* ctx, const uint8_t* rgb_host, int32_t H, int32_t W, const wowsr_hsv_range* ranges,
+                                     int32_t n_ranges, float* mask_host) {
+  if (!ctx || !rgb_host || !mask_host || !ranges || H <= 0 || W <= 0) return WOWSR_ERR_ARG;
+  DeviceGuard g(ctx->device);
+  const size_t pitch = ((size_t)W * 3 + 15) & ~(size_t)15, mpitch = ((size_t)W * 4 + 15) & ~(size_t)15;
+  if (int e = wowsr_ensure(ctx, ctx->post_in, pitch * H)) return e;
+  if (int e = wowsr_ensure(ctx, ctx->post_out, mpitch * H)) return e;
+  WCUDA(ctx, cudaMemcpy2DAsync(ctx->post_in.p, pitch, rgb_host, (size_t)W * 3, (size_t)W * 3, H, cudaMemcpyHostToDevice, 0));
+  wowsr_image in{ctx->post_in.p, (int64_t)pitch, W, H, 0, H};
+  if (int e = wowsr_green_mask(ctx, &in, ranges, n_ranges, (float*)ctx->post_out.p, (int64_t)mpitch, nullptr)) return e;
+  WCUDA(ctx, cudaMemcpy2DAsync(mask_host, (size_t)W * 4, ctx->post_out.p, mpitch, (size_t)W * 4, H, cudaMemcpyDeviceToHost, 0));
   WCUDA(ctx, cudaStreamSynchronize(0));
   return WOWSR_OK;
 }

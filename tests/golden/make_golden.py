@@ -9,6 +9,8 @@ Outputs (np.savez_compressed, all small):
   rrdb23_cfg1_64.npz                         : 23-block x4plus, 64x64 crop of BASELINE config 1 input, u8 + float
   rrdb23_cfg1_128_u8.npz                     : BASELINE config 1 (128x128, seed 0), reference uint8 output
   init_checksums.npz                         : float64 sums of the seed-0 default-init weights (RNG stream pin)
+  green_mask_u8_90x121.npz, green_mask_u16_64x80.npz : compute_green_mask_hsv (vector_extraction.py:222-270) of the unmodified
+                                               reference, its raster served by a stub rasterio.open (`python make_golden.py green`)
 """
 import os
 import sys
@@ -67,5 +69,30 @@ def main():
     print("golden fixtures written")
 
 
+def main_green():
+    """Fixtures of the HSV vegetation mask: uniform colour noise (every hue / saturation / value box edge is hit) with an
+    image-like half, default and non-default ExtractionConfig; a uint16 raster for the max-scaling branch (:245-247)."""
+    store = {}
+    ve = refload.load_vector_extraction(lambda p: store[str(p)])
+    rng = np.random.default_rng(31)
+    img = rng.integers(0, 256, (90, 121, 3), dtype=np.uint8)
+    img[45:] = (img[45:].astype(np.int32) * 3 // 8 + image_like(45, 121, seed=32).astype(np.int32) * 5 // 8).astype(np.uint8)
+    store["u8"] = [img[..., c] for c in range(3)]
+    cfg2 = dict(hsv_green_hue_range=(30, 90), hsv_saturation_min=20, hsv_value_min=50)
+    np.savez_compressed(os.path.join(HERE, "green_mask_u8_90x121.npz"), img=img,
+                        mask_default=ve.compute_green_mask_hsv("u8", ve.ExtractionConfig()),
+                        mask_cfg2=ve.compute_green_mask_hsv("u8", ve.ExtractionConfig(**cfg2)),
+                        cfg2_hue=np.array(cfg2["hsv_green_hue_range"]), cfg2_sat=cfg2["hsv_saturation_min"], cfg2_val=cfg2["hsv_value_min"])
+    raster = rng.integers(0, 9000, (64, 80, 3)).astype(np.uint16)
+    store["u16"] = [raster[..., c] for c in range(3)]
+    np.savez_compressed(os.path.join(HERE, "green_mask_u16_64x80.npz"), raster=raster,
+                        mask_default=ve.compute_green_mask_hsv("u16", ve.ExtractionConfig()))
+    print("green-mask fixtures written")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "green":
+        main_green()
+    else:
+        main()
+        main_green()

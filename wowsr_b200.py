@@ -11,4 +11,5 @@ _pkg = importlib.import_module("sentinel2-super-resolution-poc_b200")
 importlib.import_module("sentinel2-super-resolution-poc_b200.app.cnn_super_resolution")
 importlib.import_module("sentinel2-super-resolution-poc_b200.app.wow_sr")
 importlib.import_module("sentinel2-super-resolution-poc_b200.app.farm_sr")
+importlib.import_module("sentinel2-super-resolution-poc_b200.app.vector_extraction")
 sys.modules[__name__] = _pkg
