@@ -6,7 +6,7 @@
 
 #include "common.h"
 
-static std::string g_create_err;
+static thread_local std::string g_create_err;  // last wowsr_create() failure of the calling thread (no ctx to hold it)
 
 int wowsr_fail(wowsr_ctx* ctx, int code, const char* fmt, ...) {
   char buf[1024];
@@ -240,7 +240,7 @@ extern "C" void wowsr_destroy(wowsr_ctx* ctx) {
   if (!ctx) return;
   DeviceGuard g(ctx->device);
   cudaDeviceSynchronize();
-  DevBuf* bufs[] = {&ctx->hist, &ctx->luts, &ctx->post_in, &ctx->post_out, &ctx->img_in, &ctx->img_out, &ctx->img_out_f32};
+  DevBuf* bufs[] = {&ctx->hist, &ctx->luts, &ctx->post_in, &ctx->post_out, &ctx->img_in, &ctx->img_out, &ctx->img_out_f32, &ctx->trace_buf};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->d_tables) cudaFree(ctx->d_tables);
@@ -254,8 +254,17 @@ extern "C" void wowsr_destroy(wowsr_ctx* ctx) {
 extern "C" const char* wowsr_last_error(const wowsr_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 extern "C" uint64_t wowsr_launch_count(const wowsr_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+// Every key some wowsr_opt() call reads; anything else is a typo and is rejected (include/wowsr.h).
+static const char* const kOptionKeys[] = {
+    "conv_impl",   "hist_match", "mem_budget_mb",       "tc_boustrophedon", "tc_chunk32", "tc_flags",
+    "tc_force_stream", "tc_generic_epilogue", "tc_grid", "tc_no_strip", "tc_stages", "tc_trace_layer",
+    "tc_wbuf",     "trunk_dataflow", "trunk_debug",     "trunk_group",      "trunk_hilo"};
+
 extern "C" int wowsr_set_option(wowsr_ctx* ctx, const char* key, int64_t value) {
   if (!ctx || !key) return WOWSR_ERR_ARG;
+  bool known = false;
+  for (const char* k : kOptionKeys) known |= strcmp(k, key) == 0;
+  if (!known) return wowsr_fail(ctx, WOWSR_ERR_ARG, "unknown option '%s'", key);
   ctx->opts[key] = value;
   return WOWSR_OK;
 }

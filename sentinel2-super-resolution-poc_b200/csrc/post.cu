@@ -440,8 +440,9 @@ __device__ __forceinline__ float hsv_in_ranges(int r, int g, int b, const MaskK&
   h = (h * (int)hdiv[diff] + 2048) >> 12;
   if (h < 0) h += 180;
   bool in = false;
-  for (int i = 0; i < k.n; i++)
-    in |= h >= k.lo[i][0] && h <= k.hi[i][0] && s >= k.lo[i][1] && s <= k.hi[i][1] && v >= k.lo[i][2] && v <= k.hi[i][2];
+#pragma unroll
+  for (int i = 0; i < GM_MAX_RANGES; i++)  // fully unrolled: the bounds stay in the constant bank (no local copy of k)
+    in |= i < k.n && h >= k.lo[i][0] && h <= k.hi[i][0] && s >= k.lo[i][1] && s <= k.hi[i][1] && v >= k.lo[i][2] && v <= k.hi[i][2];
   return in ? 1.0f : 0.0f;
 }
 

@@ -107,3 +107,20 @@ def test_rrdbnet_container_state_dict_roundtrip(ws):
     with pytest.raises(ValueError):
         cnn.download_weights("nope")
     assert set(cnn.MODELS) == {"realesrgan_x4", "realesrgan_anime"} and cnn.MODELS["realesrgan_x4"]["blocks"] == 23
+
+
+def test_option_key_list_matches_the_keys_the_library_reads():
+    """wowsr_set_option rejects unknown keys (include/wowsr.h); its list must hold exactly the keys some wowsr_opt() reads."""
+    csrc = os.path.join(ROOT, "sentinel2-super-resolution-poc_b200", "csrc")
+    read = set()
+    for fn in os.listdir(csrc):
+        if fn.endswith((".cu", ".cuh", ".h")):
+            read |= set(re.findall(r'wowsr_opt\(\s*ctx,\s*"([a-z0-9_]+)"', open(os.path.join(csrc, fn)).read()))
+    src = open(os.path.join(csrc, "ctx.cu")).read()
+    block = src[src.index("kOptionKeys[] = {"):]
+    listed = set(re.findall(r'"([a-z0-9_]+)"', block[:block.index("};")]))
+    assert listed == read
+    for path in ("tests/test_gpu_rrdbnet.py", "tools/try_dataflow_perf.py", "tools/gpu_probe.py"):
+        text = open(os.path.join(ROOT, path)).read()
+        used = set(re.findall(r"\b((?:tc|trunk|conv|hist|mem)_[a-z0-9_]+)\s*=\s*\d", text)) | set(re.findall(r'"((?:tc|trunk|conv|hist|mem)_[a-z0-9_]+)"\s*:', text))
+        assert used <= listed, (path, used - listed)
