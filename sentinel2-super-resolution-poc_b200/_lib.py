@@ -70,6 +70,8 @@ _SIGS = {
                                      C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "wowsr_get_timing": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float), C.c_int32]),
     "wowsr_debug_trace": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
+    "wowsr_debug_fused_schedule": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                               C.POINTER(C.c_int32)]),
     "wowsr_load_edsr": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.POINTER(C.c_void_p), C.c_int32, C.c_int32]),
     "wowsr_edsr_upsample_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
 }
@@ -282,6 +284,19 @@ def gaussian_taps(sigma):
     if n < 0:
         raise ValueError("sigma too large")
     return list(buf)[:n]
+
+
+def fused_schedule(h, w, n_win, first_conv=4, lag=0):
+    """Task list of the experimental fused-tail launch (csrc/sched_plan.h) as an (n, 8) uint16 array + its info dict."""
+    L = lib()
+    info = (C.c_int32 * 8)()
+    n = L.wowsr_debug_fused_schedule(h, w, n_win, first_conv, lag, None, 0, info)
+    if n < 0:
+        raise ValueError(f"no schedule for {n_win} windows of {h}x{w} (first conv {first_conv}, lag {lag})")
+    arr = np.empty((n, 8), dtype=np.uint16)
+    L.wowsr_debug_fused_schedule(h, w, n_win, first_conv, lag, arr.ctypes.data, n, info)
+    keys = ("lag", "n_bands", "band_target_tiles", "strip_x0", "band_rows", "n_layers", "epi_warps")
+    return arr, dict(zip(keys, list(info)))
 
 
 _TABLES = {0: ("gam", np.uint16, 256), 1: ("cbrt", np.uint16, 3072), 2: ("lab_y", np.uint16, 256),

@@ -1,0 +1,26 @@
+# Round-2 queue — the experiments prepared on the CPU box after round 1's GPU budget was spent (none of them has run on
+# hardware yet).  ONE gpurun call, every step under its own timeout so a hang costs seconds, not the box:
+#   gpurun --timeout 900 -- 'bash tools/experiments/r2_queue.sh'
+# 1. tcgen05 collector / weight-stationary microbenchmark (tools/mma_ws_bench.cu): one (mode, N) per process, because an
+#    illegal shape faults the context.  Question: can B (the weights) be held across the R + 2 input rows of a tile?
+# 2. fused conv4+conv5 launch (csrc/sched_kernel.cuh): correctness on small shapes, then trunk time on 25 windows of 276x276
+#    against the layer-by-layer path, then CTA 0's per-task trace.
+# 3. DRAM traffic of both paths (is the dense buffer really found in L2?): ncu dram bytes over one forward of 2 blocks.
+# 4. the new HSV vegetation-mask kernel's tests (they also run in the round-end pytest -m gpu).
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out build
+O=gpurun_out
+[ -x build/mma_ws_bench ] || nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I sentinel2-super-resolution-poc_b200/csrc tools/mma_ws_bench.cu -o build/mma_ws_bench
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/r2_smi.txt 2>&1
+( for mode in 0 1 2 3; do for n in 32 64 96 128 192; do timeout 60 build/mma_ws_bench $mode $n || echo "mode=$mode N=$n exit $?"; done; done ) > $O/r2_mma_ws_bench.txt 2>&1
+timeout 120 python -m pytest tests/test_zz_gpu_green_mask.py -x -q -m gpu > $O/r2_green_mask_pytest.txt 2>&1
+timeout 150 python tools/try_fused.py check > $O/r2_fused_check.txt 2>&1; echo "exit $?" >> $O/r2_fused_check.txt
+if grep -q "exit 0" $O/r2_fused_check.txt; then
+  timeout 150 python tools/try_fused.py perf 4 120 > $O/r2_fused_perf.txt 2>&1; echo "exit $?" >> $O/r2_fused_perf.txt
+  timeout 60 python tools/try_fused.py trace 4 120 > $O/r2_fused_trace.txt 2>&1; echo "exit $?" >> $O/r2_fused_trace.txt
+  for fuse in 0 4; do
+    timeout 240 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:'conv3x3_tc|rdb_fused' \
+      --csv --log-file $O/r2_dram_fuse$fuse.csv python tools/try_fused_ncu.py $fuse > $O/r2_dram_fuse$fuse.log 2>&1
+  done
+fi
+echo done
