@@ -539,6 +539,20 @@ int run_rdb_fused(wowsr_ctx* ctx, ConvNet* net, int rdb, int nb, int h, int w, c
   WCUDA(ctx, cudaMemsetAsync(net->trunk_ctr.p, 0, ctr_bytes, st));
   rdb_fused_kernel<<<grid, TC_THREADS, smem, st>>>(tm[0][0], tm[0][1], tm[1][0], tm[1][1], T);
   WLAUNCH_CHECK(ctx);
+  if (wowsr_opt(ctx, "trunk_debug", 0)) {  // bring-up aid: band counters after the launch (all must equal the target) + watchdog code
+    std::vector<unsigned int> c(ctr_bytes / 4);
+    int flag = 0;
+    cudaError_t ce = cudaStreamSynchronize(st);
+    cudaMemcpy(c.data(), net->trunk_ctr.p, ctr_bytes, cudaMemcpyDeviceToHost);
+    cudaMemcpy(&flag, net->err.p, 4, cudaMemcpyDeviceToHost);
+    size_t short_of = 0, first = c.size();
+    for (size_t i = 0; i < c.size(); i++)
+      if (c[i] != T.band_target) { if (!short_of++) first = i; }
+    fprintf(stderr, "[trunk_debug] rdb %d: sync=%s watchdog=%d grid=%d tasks=%d lag=%d bands=%d target=%u; %zu of %zu counters off target",
+            rdb, cudaGetErrorString(ce), flag, grid, T.n_tasks, net->sched_key[4], T.n_bands, T.band_target, short_of, c.size());
+    if (short_of) fprintf(stderr, " (first: slot %zu window %zu band %zu = %u)", first / ((size_t)nb * T.n_bands), first / T.n_bands % nb, first % T.n_bands, c[first]);
+    fprintf(stderr, "\n");
+  }
   return 0;
 }
 
