@@ -487,7 +487,7 @@ int run_rdb_fused(wowsr_ctx* ctx, ConvNet* net, int rdb, int nb, int h, int w, c
                   const CUtensorMap (&tm)[2][2], cudaStream_t st) {
   const int n_rdb = 3 * net->num_block;
   const int k_first = (int)wowsr_opt(ctx, "trunk_fuse", 4) - 1;
-  const int lag = (int)wowsr_opt(ctx, "trunk_lag", 120);
+  const int lag = (int)wowsr_opt(ctx, "trunk_lag", 0);  // 0: automatic (legal minimum for this window shape + latency slack)
   if (k_first < 0 || k_first > 3) return wowsr_fail(ctx, WOWSR_ERR_ARG, "trunk_fuse must be 1..4 (first fused conv, 1-based)");
   if (!net->trunk_tab.p) {
     for (int i = 0; i < n_rdb * 5; i++)
@@ -500,7 +500,7 @@ int run_rdb_fused(wowsr_ctx* ctx, ConvNet* net, int rdb, int nb, int h, int w, c
   const int key[5] = {nb, h, w, k_first, lag};
   if (memcmp(key, net->sched_key, sizeof key) != 0 || !net->sched_tasks.p) {  // (re)build the task list for this batch shape
     SchedPlan P;
-    if (!sched_build(P, h, w, nb, k_first, lag) && !sched_build(P, h, w, nb, k_first, 0, lag))
+    if (!sched_build(P, h, w, nb, k_first, lag) && !sched_build(P, h, w, nb, k_first, 0, lag > 48 ? lag : 48, 0))
       return wowsr_fail(ctx, WOWSR_ERR_UNSUPPORTED, "no fused-tail schedule for %d windows of %dx%d", nb, h, w);
     if (P.strip_x0 != fl.x0) return wowsr_fail(ctx, WOWSR_ERR_STATE, "schedule and trunk layout disagree on the strip (%d vs %d)", P.strip_x0, fl.x0);
     if (int e = wowsr_ensure(ctx, net->sched_tasks, P.tasks.size() * sizeof(SchedTask))) return e;
@@ -845,7 +845,8 @@ extern "C" int32_t wowsr_debug_trace(wowsr_ctx* ctx, int64_t* out, int32_t cap) 
 extern "C" int32_t wowsr_debug_fused_schedule(int32_t h, int32_t w, int32_t n_win, int32_t first_conv, int32_t lag, uint16_t* tasks,
                                               int32_t cap, int32_t* info) {
   SchedPlan P;
-  if (!sched_build(P, h, w, n_win, first_conv - 1, lag)) return WOWSR_ERR_UNSUPPORTED;
+  if (!(lag == -1 ? sched_build(P, h, w, n_win, first_conv - 1, 0, 48, 0) : sched_build(P, h, w, n_win, first_conv - 1, lag)))
+    return WOWSR_ERR_UNSUPPORTED;
   if (info) {
     info[0] = P.lag; info[1] = P.n_bands; info[2] = P.band_target_tiles; info[3] = P.strip_x0;
     info[4] = P.band_rows; info[5] = P.n_layers; info[6] = TC_EPI_WARPS; info[7] = 0;

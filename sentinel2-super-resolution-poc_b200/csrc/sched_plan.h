@@ -99,9 +99,11 @@ inline bool producers_precede_consumers(const SchedPlan& P) {
 
 }  // namespace sched_detail
 
-// Builds the plan; `lag` <= 0 picks the smallest multiple of 8 steps that is both legal (producers precede consumers) and at
-// least `min_lag`.  Returns false when the shape cannot be scheduled (no band structure: h < 8).
-inline bool sched_build(SchedPlan& P, int h, int w, int n_win, int k_first, int lag, int min_lag = 48) {
+// Builds the plan.  `lag` > 0 is taken literally (false if it is not legal).  `lag` <= 0 is automatic: the smallest legal
+// multiple of 8 steps (producers precede consumers; >= `min_lag`) plus `slack_tasks` tasks' worth of steps, so that a consumer's
+// last producer is more than one machine-full of tasks (148 CTAs) behind it and the publish -> poll -> TMA latency is hidden;
+// slack_tasks = 0 returns the legal minimum itself.  Returns false when the shape cannot be scheduled (no band structure: h < 8).
+inline bool sched_build(SchedPlan& P, int h, int w, int n_win, int k_first, int lag, int min_lag = 48, int slack_tasks = 240) {
   using namespace sched_detail;
   if (h < 8 || w < 1 || n_win < 1 || n_win > 65535 || h > 65000 || w > 65000 || k_first < 0 || k_first > 3) return false;
   P.h = h; P.w = w; P.n_win = n_win; P.k_first = k_first; P.n_layers = 5 - k_first;
@@ -130,7 +132,13 @@ inline bool sched_build(SchedPlan& P, int h, int w, int n_win, int k_first, int 
         const size_t nk = per[i].size();
         for (size_t j = (size_t)u * nk / n0; j < (size_t)(u + 1) * nk / n0; j++) P.tasks.push_back(per[i][j]);
       }
-    if (producers_precede_consumers(P)) return true;
+    if (producers_precede_consumers(P)) {
+      if (lag > 0 || slack_tasks <= 0 || try_lag >= (int)n0) return true;
+      const int tasks_per_step = P.n_layers + 1;  // one tile of every N = 32 conv + two 4-row tiles of conv5
+      int want = try_lag + (slack_tasks + tasks_per_step - 1) / tasks_per_step;
+      if (want > (int)n0) want = (int)n0;
+      return sched_build(P, h, w, n_win, k_first, want, min_lag, 0);  // a longer lag only delays consumers: still legal
+    }
     if (lag > 0 || try_lag >= (int)n0) return false;  // an explicit lag is taken literally
   }
 }

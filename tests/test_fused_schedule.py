@@ -23,7 +23,7 @@ def _out_rect(t, h, w):
     return t[V0], min(t[V0] + R, h), t[U0], min(t[U0] + 128, w)
 
 
-SHAPES = [(276, 276, 2, 1, 0), (276, 276, 3, 4, 0), (276, 276, 3, 4, 120), (276, 276, 2, 3, 0), (276, 276, 2, 2, 0), (532, 532, 2, 4, 120),
+SHAPES = [(276, 276, 8, 4, 0), (276, 276, 2, 1, 0), (276, 276, 3, 4, 0), (276, 276, 3, 4, 120), (276, 276, 2, 3, 0), (276, 276, 2, 2, 0), (532, 532, 2, 4, 120), (532, 532, 3, 4, 0),
           (148, 148, 9, 4, 0), (40, 48, 1, 4, 0), (300, 290, 1, 4, 0), (150, 276, 2, 4, 0), (64, 128, 2, 4, 0), (9, 1000, 1, 2, 0)]
 
 
@@ -72,9 +72,11 @@ def test_schedule_is_complete_and_safe(ws, h, w, n_win, first, lag):
             done[row[K], row[WIN], sl] += 1
             last_pub_index[row[K], row[WIN], sl] = i
     assert min(slack) >= 1
-    if lag >= 120 and len(t) > 2000:
-        # the point of the skew: a consumer's last producer is more than one full machine of tasks (148 CTAs) behind it
-        assert min(slack) > 148, min(slack)
+    if ((lag >= 120 and w <= 276) or lag == 0) and len(t) > 1500:
+        # the point of the skew: a consumer's last producer is more than one full machine of tasks (148 CTAs) behind it —
+        # everywhere but in the fill phase at the head of the list, where only the first conv has tiles to interleave
+        slack = np.array(slack)
+        assert np.median(slack) >= 240 and (slack <= 148).mean() < 0.02, (np.median(slack), (slack <= 148).mean())
 
 
 @pytest.mark.parametrize("grid", [1, 3, 7, 148])
@@ -122,5 +124,7 @@ def test_unschedulable_shapes_and_lags_are_refused(ws):
     for first in (0, 5):                              # conv5 alone is not a fusion; there is no conv0
         with pytest.raises(ValueError):
             ws._lib.fused_schedule(276, 276, 1, first, 0)
-    _, info = ws._lib.fused_schedule(276, 276, 25, 4, 0)
-    assert info["lag"] % 8 == 0 and info["lag"] >= 48
+    legal_min = ws._lib.fused_schedule(276, 276, 25, 4, -1)[1]["lag"]
+    auto = ws._lib.fused_schedule(276, 276, 25, 4, 0)[1]["lag"]
+    assert legal_min % 8 == 0 and legal_min >= 48
+    assert auto == legal_min + 80                      # 240 tasks of slack at 3 tasks per step (conv4 tile + two conv5 tiles)

@@ -16,8 +16,8 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O
 timeout 120 python -m pytest tests/test_zz_gpu_green_mask.py -x -q -m gpu > $O/r2_green_mask_pytest.txt 2>&1
 timeout 150 python tools/try_fused.py check > $O/r2_fused_check.txt 2>&1; echo "exit $?" >> $O/r2_fused_check.txt
 if grep -q "exit 0" $O/r2_fused_check.txt; then
-  timeout 150 python tools/try_fused.py perf 4 120 > $O/r2_fused_perf.txt 2>&1; echo "exit $?" >> $O/r2_fused_perf.txt
-  timeout 60 python tools/try_fused.py trace 4 120 > $O/r2_fused_trace.txt 2>&1; echo "exit $?" >> $O/r2_fused_trace.txt
+  timeout 150 python tools/try_fused.py perf 4 0 > $O/r2_fused_perf.txt 2>&1; echo "exit $?" >> $O/r2_fused_perf.txt
+  timeout 60 python tools/try_fused.py trace 4 0 > $O/r2_fused_trace.txt 2>&1; echo "exit $?" >> $O/r2_fused_trace.txt
   for fuse in 0 4; do
     timeout 240 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:'conv3x3_tc|rdb_fused' \
       --csv --log-file $O/r2_dram_fuse$fuse.csv python tools/try_fused_ncu.py $fuse > $O/r2_dram_fuse$fuse.log 2>&1

@@ -61,7 +61,7 @@ def perf(fuse, lag):
     img = np.random.default_rng(1).integers(0, 256, (1044, 1044, 3), dtype=np.uint8)   # 5 x 5 windows of 276 x 276
     print("layer-by-layer")
     a, _ = run(tensors, blocks, img, 256, reps=3)
-    for f, l in ((fuse, lag), (fuse, 60), (fuse, 240), (3, lag)):
+    for f, l in ((fuse, lag), (fuse, 64), (fuse, 240), (3, lag)):
         print(f"fused tail: convs {f}..5, lag {l}")
         try:
             b, _ = run(tensors, blocks, img, 256, reps=3, trunk_fuse=f, trunk_lag=l)
@@ -89,5 +89,5 @@ def trace(fuse, lag):
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "check"
     fuse = int(sys.argv[2]) if len(sys.argv) > 2 else 4
-    lag = int(sys.argv[3]) if len(sys.argv) > 3 else 120
+    lag = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     sys.exit({"check": check, "perf": lambda: perf(fuse, lag), "trace": lambda: trace(fuse, lag)}[mode]())

@@ -18,7 +18,6 @@ img = np.random.default_rng(1).integers(0, 256, (1044, 1044, 3), dtype=np.uint8)
 h = ws.Handle(0)
 if fuse:
     h.set_option("trunk_fuse", fuse)
-    h.set_option("trunk_lag", 120)
 h.load_rrdbnet(tensors, blocks, precision="bf16")
 h.enhance_host(img, 256)
 print(h.timing())
