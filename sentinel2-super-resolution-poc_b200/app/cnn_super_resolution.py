@@ -240,3 +240,60 @@ class RealESRGAN:
 
     def _tile_process(self, img):  # kept for interface parity; the planner + stitching are native
         raise NotImplementedError("tiling runs inside libwowsr (wowsr_plan_windows / wowsr_rrdbnet_forward_windows)")
+
+
+def apply_cnn_sr(input_path: Path, output_path: Path, scale: int = 4):
+    """Same signature, outputs and metadata as the reference's file entry point (:283-375, called by sr_cli.py:115-124).
+    GeoTIFF input: bands 1-3 (or one band replicated), non-uint8 rasters min-max stretched with the reference's ``+ 1e-6``
+    (:308-311) on the device, RGB->BGR, ``enhance``, GeoTIFF out with the transform scaled.  Any other file: ``cv2.imread``
+    (BGR) -> ``enhance`` -> PNG."""
+    import cv2
+
+    from . import wow_sr
+    input_path = Path(input_path)
+    is_tif = input_path.suffix.lower() in (".tif", ".tiff")
+    transform = crs = None
+    model = RealESRGAN(scale=scale, tile_size=256)
+    if is_tif:
+        img, transform, crs = wow_sr.read_image(input_path)                 # RGB, file dtype
+        host = np.ascontiguousarray(img)
+        if host.dtype == np.uint16:
+            host = host.astype(np.int32)
+        x = wow_sr.normalise_to_uint8_cuda(torch.from_numpy(host).to(model.device), eps=1e-6)
+        in_shape = img.shape
+        out_bgr = model.enhance_cuda(x.flip(2).contiguous())                # RGB -> BGR (:318-322)
+        output_rgb = out_bgr.flip(2).contiguous().cpu().numpy()
+        output_bgr = None
+    else:
+        img = cv2.imread(str(input_path))
+        if img is None:
+            raise FileNotFoundError(str(input_path))
+        in_shape = img.shape
+        output_bgr = model.enhance(img)
+        output_rgb = output_bgr[:, :, ::-1]
+    output_path = Path(output_path)
+    output_path.parent.mkdir(parents=True, exist_ok=True)
+    if transform is not None:
+        import rasterio
+        from rasterio.transform import Affine
+        new_transform = Affine(transform.a / scale, transform.b, transform.c, transform.d, transform.e / scale, transform.f)
+        final_path = output_path.with_suffix(".tif")
+        with rasterio.open(final_path, "w", driver="GTiff", height=output_rgb.shape[0], width=output_rgb.shape[1], count=3,
+                           dtype="uint8", crs=crs, transform=new_transform, compress="lzw") as dst:
+            for i in range(3):
+                dst.write(output_rgb[:, :, i], i + 1)
+    else:
+        final_path = output_path.with_suffix(".png")
+        if output_bgr is None:  # a GeoTIFF without georeferencing: the reference writes its BGR result (:361-362)
+            output_bgr = np.ascontiguousarray(output_rgb[:, :, ::-1])
+        cv2.imwrite(str(final_path), output_bgr)
+    metadata = {
+        "model": f"RealESRGAN_x{scale}",
+        "scale": scale,
+        "input_size": [in_shape[1], in_shape[0]],
+        "output_size": [output_rgb.shape[1], output_rgb.shape[0]],
+        "device": str(model.device),
+        "original_resolution_m": 10.0,
+        "effective_resolution_m": 10.0 / scale,
+    }
+    return final_path, metadata

@@ -50,14 +50,15 @@ def wow_sr_array(img_rgb: np.ndarray, upsampler, enhance_crops: bool = True) -> 
 # IO glue of the /api/wow path
 # ---------------------------------------------------------------------------------------------
 
-def normalise_to_uint8_cuda(img: torch.Tensor) -> torch.Tensor:
+def normalise_to_uint8_cuda(img: torch.Tensor, eps: float = 0.0) -> torch.Tensor:
     """The reference's raster normalisation (:66-72) on the device, bit-exact with numpy: rasters whose maximum exceeds
-    255 are min-max stretched in float64 and truncated; everything else is cast (wrapping, like ``astype``)."""
+    255 are min-max stretched in float64 and truncated; everything else is cast (wrapping, like ``astype``).
+    ``eps`` is the ``+ 1e-6`` that ``apply_cnn_sr`` adds to the range (cnn_super_resolution.py:310)."""
     if img.dtype == torch.uint8:
         return img
     mx, mn = img.max(), img.min()
     if float(mx) > 255:
-        return ((img - mn).to(torch.float64) / (mx - mn).to(torch.float64) * 255).to(torch.uint8)
+        return ((img - mn).to(torch.float64) / ((mx - mn).to(torch.float64) + eps) * 255).to(torch.uint8)
     return img.to(torch.int64).to(torch.uint8)
 
 

@@ -37,6 +37,21 @@ def test_normalise_matches_reference_arithmetic(ws, case):
     assert got.dtype == np.uint8 and np.array_equal(got, want)
 
 
+def test_normalise_with_the_cnn_sr_epsilon(ws):
+    """apply_cnn_sr stretches with ``+ 1e-6`` in the denominator (cnn_super_resolution.py:308-311): the maximum maps to 254."""
+    rng = np.random.default_rng(12)
+    for a in (rng.integers(0, 10000, (31, 17, 3)).astype(np.uint16), rng.integers(100, 300, (9, 9, 3)).astype(np.uint16),
+              rng.integers(0, 200, (9, 9, 3)).astype(np.uint16)):
+        img = a
+        if img.max() > 255:
+            img = (img - img.min()) / (img.max() - img.min() + 1e-6) * 255
+        want = img.astype(np.uint8)
+        got = ws.app.wow_sr.normalise_to_uint8_cuda(torch.from_numpy(a.astype(np.int32)), eps=1e-6).numpy()
+        assert np.array_equal(got, want)
+        if a.max() > 255:
+            assert got.max() == 254
+
+
 @pytest.mark.gpu
 def test_apply_wow_sr_files_metadata_and_residency(ws, tmp_path, monkeypatch):
     import cv2
