@@ -28,5 +28,6 @@ if grep -q "exit 0" $O/r2_fused_check.txt; then
     timeout 240 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:'conv3x3_tc|rdb_fused' \
       --csv --log-file $O/r2_dram_fuse$fuse.csv python tools/try_fused_ncu.py $fuse > $O/r2_dram_fuse$fuse.log 2>&1
   done
+  python tools/dram_compare.py $O/r2_dram_fuse0.csv $O/r2_dram_fuse4.csv > $O/r2_dram_compare.txt 2>&1
 fi
 echo done
