@@ -29,6 +29,22 @@ SHAPES = [(276, 276, 8, 4, 0), (276, 276, 2, 1, 0), (276, 276, 3, 4, 0), (276, 2
 
 @pytest.mark.parametrize("h,w,n_win,first,lag", SHAPES)
 def test_schedule_is_complete_and_safe(ws, h, w, n_win, first, lag):
+    _check_schedule(ws, h, w, n_win, first, lag)
+
+
+def test_schedule_random_shapes(ws):
+    """Property test over random window shapes (ragged widths with and without a remainder strip, partial last bands)."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(h=st.integers(8, 300), w=st.integers(1, 600), n_win=st.integers(1, 3), first=st.integers(1, 4), lag=st.sampled_from([0, -1]))
+    def run(h, w, n_win, first, lag):
+        _check_schedule(ws, h, w, n_win, first, lag)
+
+    run()
+
+
+def _check_schedule(ws, h, w, n_win, first, lag):
     arr, info = ws._lib.fused_schedule(h, w, n_win, first, lag)
     t = _decode(arr)
     nb, br, x0 = info["n_bands"], info["band_rows"], info["strip_x0"]
