@@ -11,6 +11,7 @@
 #include "conv_kernels.cuh"
 #include "trunk_kernel.cuh"
 #include "sched_kernel.cuh"
+#include "ups_kernel.cuh"
 
 namespace {
 
@@ -219,6 +220,32 @@ int make_tmap(wowsr_ctx* ctx, CUtensorMap* m, const void* base, int C, int W, in
   return 0;
 }
 
+// EXPERIMENTAL (ups_kernel.cuh): 5-D map of the x-upsampled view of an NHWC buffer [Nw][Hs][Ws][C]: dims (C, rep = 2 with a
+// ZERO stride, Ws, Hs, Nw), box (64 ch, 2, 66 source pixels, 1 row, 1 window) = 132 upsampled pixels.  `transposed`: the run
+// axis (the replicated one) walks y, for the vertical tiles.  Whether the driver accepts a zero stride is what
+// tools/tma_stride0_probe.cu measures; a rejection surfaces here as an error, never as a silent fallback.
+int make_tmap_ups(wowsr_ctx* ctx, CUtensorMap* m, const void* base, int C, int Ws, int Hs, int Nw, bool fp16, bool transposed) {
+  auto enc = get_encode();
+  if (!enc) return wowsr_fail(ctx, WOWSR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t dims[5] = {(cuuint64_t)C, 2, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)Nw};
+  cuuint64_t strides[4] = {0, (cuuint64_t)C * 2, (cuuint64_t)C * 2 * Ws, (cuuint64_t)C * 2 * Ws * Hs};
+  if (transposed) {
+    dims[2] = (cuuint64_t)Hs;
+    dims[3] = (cuuint64_t)Ws;
+    strides[1] = (cuuint64_t)C * 2 * Ws;
+    strides[2] = (cuuint64_t)C * 2;
+  }
+  cuuint32_t box[5] = {64u, 2u, 66u, 1u, 1u};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return wowsr_fail(ctx, WOWSR_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled rejected the zero-stride upsample map (C=%d,Ws=%d,Hs=%d,N=%d): CUresult %d",
+                      C, Ws, Hs, Nw, (int)r);
+  return 0;
+}
+
 struct LayerIO {
   const void* in = nullptr;  // activation buffer (T), C_total channels per pixel
   int in_C = 0;
@@ -235,6 +262,7 @@ struct LayerIO {
   void* out_t = nullptr;
   int out_stride = 0, out_choff = 0, out_rep = 1;
   int out_ps = 0;
+  int in_ups = 0;  // experimental: `in` is at HALF the layer resolution, the nearest-x2 upsample is folded into the tensor maps
   float final_scale = 255.0f;
   float final_add[3] = {0.0f, 0.0f, 0.0f};
   int final_round = 0;
@@ -326,6 +354,11 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
     return 0;
   }
   CUtensorMap tmap, tmap_v, tmap32, tmap_v32;
+  if (io.in_ups) {
+    if (L.cin != 64 || N != 64 || !P.w_resident || (io.w & 1) || (io.h & 1) || io.in_C != 64 || P.ident)
+      return wowsr_fail(ctx, WOWSR_ERR_UNSUPPORTED, "folded upsample: 64 -> 64 layers at an even resolution only");
+    if (int e = make_tmap_ups(ctx, &tmap, io.in, 64, io.w / 2, io.h / 2, io.Nw, L.fp16, false)) return e;
+  } else
   if (int e = make_tmap(ctx, &tmap, io.in, io.in_C, io.w, io.h, io.Nw, L.fp16, false)) return e;
   tmap_v = tmap;
   const bool has_half = L.cin % 64 == 32 || P.chunk_ch == 32;  // 32-channel chunks: their own 32-channel / SWIZZLE_64B maps
@@ -343,7 +376,9 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
     const int v_runs = (io.h + TC_RUN - 1) / TC_RUN, v_rows = (rem + R - 1) / R;
     const double eff_h = rem / (double)TC_RUN;
     const double eff_v = (io.h / (double)(v_runs * TC_RUN)) * (rem / (double)(v_rows * R));
-    if (eff_v > eff_h && max_grid >= 2 && make_tmap(ctx, &tmap_v, io.in, io.in_C, io.w, io.h, io.Nw, L.fp16, true) == 0 &&
+    if (eff_v > eff_h && max_grid >= 2 &&
+        (io.in_ups ? make_tmap_ups(ctx, &tmap_v, io.in, 64, io.w / 2, io.h / 2, io.Nw, L.fp16, true)
+                   : make_tmap(ctx, &tmap_v, io.in, io.in_C, io.w, io.h, io.Nw, L.fp16, true)) == 0 &&
         (!has_half || make_tmap(ctx, &tmap_v32, io.in, io.in_C, io.w, io.h, io.Nw, L.fp16, true, true) == 0)) {
       use_v = true;
       P.strip_x0 = wm;
@@ -373,6 +408,14 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
     }
   }
   size_t smem = (size_t)P.n_stage * P.astage + (size_t)P.n_wbuf * chunk_bytes + id_bytes + SMEM_SLACK;
+  if (io.in_ups) {  // experimental folded-upsample kernel (ups_kernel.cuh): plain epilogue only
+    if (P.final || P.res1 || P.res2 || P.out_f32_a || P.out_f32_b || P.lo_in || P.lo_out || P.out_rep != 1 || P.out_ps || !P.out_t)
+      return wowsr_fail(ctx, WOWSR_ERR_UNSUPPORTED, "folded upsample: plain epilogue only");
+    WCUDA(ctx, cudaFuncSetAttribute(conv3x3_tc_ups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+    conv3x3_tc_ups_kernel<<<grid, TC_THREADS, smem, st>>>(tmap, tmap_v, P);
+    WLAUNCH_CHECK(ctx);
+    return 0;
+  }
   // epilogue specialisation (conv_kernels.cuh): the generic path handles every other layer shape
   int mode = EPI_GENERIC;
   if (!wowsr_opt(ctx, "tc_generic_epilogue", 0) && N >= 32 && !P.final && P.out_t && P.out_rep == 1 && !P.out_ps && !P.out_f32_b &&
@@ -683,23 +726,27 @@ int rrdbnet_batch(wowsr_ctx* ctx, ConvNet* net, const uint8_t* img, long long pi
       std::swap(cur, nxt);
     }
   WCUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+  // experimental (ups_kernel.cuh): producers store at their own resolution, the upsample convs replicate through their tensor maps
+  const int fold = wowsr_opt(ctx, "tail_fold_upsample", 0) && wowsr_opt(ctx, "conv_impl", 0) == 0 ? 1 : 0;
   {  // conv_body + long skip, written nearest-x2 replicated for conv_up1
     LayerIO io;
     io.in = cur; io.in_C = 192; io.Nw = nb; io.h = h; io.w = w;
     io.f32 = fl;
     io.scale1 = 1.0f; io.res1 = (const float*)net->feat.p;
-    io.out_t = net->up1.p; io.out_stride = 64; io.out_rep = 2; io.out_fp16 = tail16;
+    io.out_t = net->up1.p; io.out_stride = 64; io.out_rep = fold ? 1 : 2; io.out_fp16 = tail16;
     if (int e = run_conv(ctx, net, net->layers[li++], io, st)) return e;
   }
   {  // conv_up1 @2x + lrelu, replicated for conv_up2
     LayerIO io;
     io.in = net->up1.p; io.in_C = 64; io.Nw = nb; io.h = 2 * h; io.w = 2 * w;
-    io.act = 1; io.out_t = net->hra.p; io.out_stride = 64; io.out_rep = 2; io.out_fp16 = tail16;
+    io.in_ups = fold;
+    io.act = 1; io.out_t = net->hra.p; io.out_stride = 64; io.out_rep = fold ? 1 : 2; io.out_fp16 = tail16;
     if (int e = run_conv(ctx, net, net->layers[li++], io, st)) return e;
   }
   {  // conv_up2 @4x + lrelu
     LayerIO io;
     io.in = net->hra.p; io.in_C = 64; io.Nw = nb; io.h = 4 * h; io.w = 4 * w;
+    io.in_ups = fold;
     io.act = 1; io.out_t = net->hrb.p; io.out_stride = 64; io.out_fp16 = tail16;
     if (int e = run_conv(ctx, net, net->layers[li++], io, st)) return e;
   }

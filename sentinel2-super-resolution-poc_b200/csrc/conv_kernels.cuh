@@ -675,7 +675,8 @@ struct IssueState {
 // warp-level reconvergence points between MMAs); otherwise the whole warp runs it and `leader` gates the issue.
 // IDENT (first chunk only): after the taps of an input row that is also an output row, one more centre-tap K-sweep with
 // B = (1/scale1) * I adds the hi part of the residual trunk (channels [0,64) of this very chunk) to that row's accumulators.
-template <int N, int R, bool FIRST, bool HALF, bool SINGLE, bool IDENT = false>
+// ROWB = bytes between the two rows of a stage (TC_ABYTES; the folded-upsample stages of ups_kernel.cuh hold 132-pixel rows).
+template <int N, int R, bool FIRST, bool HALF, bool SINGLE, bool IDENT = false, int ROWB = TC_ABYTES>
 __device__ __forceinline__ void issue_chunk(const ConvParams& P, IssueState& S, bool leader, bool committer, bool last_chunk,
                                             uint32_t full0, uint32_t empty0, uint64_t adesc0, uint64_t bd, uint32_t acc_base,
                                             uint32_t idesc_base, uint64_t id_desc = 0) {
@@ -696,7 +697,7 @@ __device__ __forceinline__ void issue_chunk(const ConvParams& P, IssueState& S, 
       const uint32_t idesc = idesc_base | ((uint32_t)(((jhi - jlo + 1) * N) >> 3) << 17);
       const uint32_t col = acc_base + (yy - 2 + jlo) * N;
       // second row of the stage: 130 pixels further; operand rows are 128 B (full chunk) or 64 B (32-ch chunk)
-      const uint64_t ad = ad0 + (uint64_t)(half * (HALF ? (TC_ABYTES >> 5) : (TC_ABYTES >> 4)));
+      const uint64_t ad = ad0 + (uint64_t)(half * (HALF ? (ROWB >> 5) : (ROWB >> 4)));
       const uint64_t bj = bd + (uint64_t)(jlo * N * (HALF ? 4 : 8));
       if (leader) issue_taps01<N, NKS, SW, FIRST>(acc_base, yy, jlo, jhi, col, ad, bd, bj, idesc, idesc_base);
       if (half == 1 && !last) {  // prefetch-wait for the next stage, hidden behind the MMAs queued above
@@ -717,11 +718,14 @@ __device__ __forceinline__ void issue_chunk(const ConvParams& P, IssueState& S, 
 }
 
 // The MMA issuer role for all tiles of this CTA.
-template <int N, int R, bool SINGLE>
+// UPS (ups_kernel.cuh): the stage rows hold the x-replicated source starting one pixel early (132 pixels), so the A
+// descriptors start 128 B into the row and the second row of a stage is TC_UPS_ROWB further.
+constexpr int TC_UPS_ROWB = 132 * 128;
+template <int N, int R, bool SINGLE, bool UPS = false>
 __device__ __forceinline__ void mma_issuer(const ConvParams& P, TcSmemCtl* ctl, bool leader, bool committer, uint32_t a_smem,
                                            uint32_t w_smem, uint32_t id_smem, uint32_t tmem_base, int n_my) {
   const uint64_t id_desc = ptx::smem_desc_sw128(id_smem, 1024, 0), id_desc64 = ptx::smem_desc_sw64(id_smem, 512);
-  const uint64_t adesc128 = ptx::smem_desc_sw128(a_smem, 1024, 0), bdesc128 = ptx::smem_desc_sw128(w_smem, 1024, 0);
+  const uint64_t adesc128 = ptx::smem_desc_sw128(a_smem + (UPS ? 128u : 0u), 1024, 0), bdesc128 = ptx::smem_desc_sw128(w_smem, 1024, 0);
   const uint64_t adesc64 = ptx::smem_desc_sw64(a_smem, 512), bdesc64 = ptx::smem_desc_sw64(w_smem, 512);
   const uint32_t full0 = ptx::smem_u32(&ctl->a_full[0]), empty0 = ptx::smem_u32(&ctl->a_empty[0]);
   const uint32_t idesc_base = P.idesc_base;
@@ -753,7 +757,7 @@ __device__ __forceinline__ void mma_issuer(const ConvParams& P, TcSmemCtl* ctl, 
       const bool ident = N == 64 && P.ident && c * P.chunk_ch < 64;
       const uint64_t idd = half_chunk ? id_desc64 + (uint64_t)(c * (4096 >> 4)) : id_desc;
 #define WOWSR_CHUNK(F, H, I) \
-  issue_chunk<N, R, F, H, SINGLE, I>(P, S, leader, committer, last_chunk, full0, empty0, adesc0, bd, acc_base, idesc_base, idd)
+  issue_chunk<N, R, F, H, SINGLE, I, (UPS ? TC_UPS_ROWB : TC_ABYTES)>(P, S, leader, committer, last_chunk, full0, empty0, adesc0, bd, acc_base, idesc_base, idd)
       if constexpr (N == 64) {
         if (ident) {
           if (c == 0) { if (half_chunk) WOWSR_CHUNK(true, true, true); else WOWSR_CHUNK(true, false, true); }

@@ -307,3 +307,22 @@ def test_experimental_fused_tail_matches_layer_by_layer(ws):
         u8_d, f_d = run(**opts)
         assert np.abs(f - f_d).max() < tol and np.abs(f_d - ref_f).max() < 4 * tol, opts
         assert (np.abs(u8.astype(int) - u8_d.astype(int)) <= 1).mean() >= 0.999, opts
+
+
+@pytest.mark.skipif(os.environ.get("WOWSR_TEST_FOLD") != "1",
+                    reason="experimental folded upsample (csrc/ups_kernel.cuh): round-2 work in progress, not yet run on hardware, opt-in")
+def test_experimental_folded_upsample_is_bit_identical(ws):
+    """conv_up1 / conv_up2 reading the source-resolution buffer through a zero-stride tensor map see exactly the operands the
+    product path reads from its replicated buffers: outputs must be bit-identical."""
+    blocks = 1
+    sd = R.calibrate_conv_last(R.random_init_state_dict(4, blocks), blocks)
+    for shape, tile in (((150, 276), 256), ((300, 290), 128), ((40, 48), 256)):
+        img = np.random.default_rng(13).integers(0, 256, shape + (3,), dtype=np.uint8)
+        outs = []
+        for fold in (0, 1):
+            h = ws.Handle(0)
+            h.set_option("tail_fold_upsample", fold)
+            h.load_rrdbnet(_tensors(sd, blocks), blocks, precision="bf16")
+            outs.append(h.enhance_host(img, tile, want_float=True))
+            h.close()
+        assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]), (shape, tile)

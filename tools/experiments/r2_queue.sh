@@ -9,6 +9,7 @@
 # 4. the new HSV vegetation-mask kernel's tests (they also run in the round-end pytest -m gpu).
 # 5. CTA-pair MMA rate (tools/mma_2cta_bench.cu): does cta_group::2 reach max(N/2, 32 + N/8) cycles (48 at N_eff = 96)?
 # 6. TMA zero-stride probe (tools/tma_stride0_probe.cu): can the nearest-x2 upsample be folded into the consumer's tensor map?
+#    and, if so, the kernel built on it (csrc/ups_kernel.cuh, option tail_fold_upsample): bit-identical output, tail time.
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out build
 O=gpurun_out
@@ -19,6 +20,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O
 ( for mode in 0 1 2 3; do for n in 32 64 96 128 192; do timeout 60 build/mma_ws_bench $mode $n || echo "mode=$mode N=$n exit $?"; done; done ) > $O/r2_mma_ws_bench.txt 2>&1
 ( for n in 32 64 96 128 192; do timeout 60 build/mma_2cta_bench $n || echo "N=$n exit $?"; done ) > $O/r2_mma_2cta_bench.txt 2>&1
 timeout 30 build/tma_stride0_probe > $O/r2_tma_stride0_probe.txt 2>&1; echo "exit $?" >> $O/r2_tma_stride0_probe.txt
+timeout 150 python tools/try_fused.py fold > $O/r2_fold_upsample.txt 2>&1; echo "exit $?" >> $O/r2_fold_upsample.txt
 timeout 120 python -m pytest tests/test_zz_gpu_green_mask.py -x -q -m gpu > $O/r2_green_mask_pytest.txt 2>&1
 timeout 150 python tools/try_fused.py check > $O/r2_fused_check.txt 2>&1; echo "exit $?" >> $O/r2_fused_check.txt
 if grep -q "exit 0" $O/r2_fused_check.txt; then

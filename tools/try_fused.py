@@ -5,6 +5,7 @@ size, then the per-task trace of CTA 0.  Written after round 1's GPU budget was 
     python tools/try_fused.py check                # 1 block: 300x290 untiled, 9 windows of 148x148, 6 windows of 276 wide
     python tools/try_fused.py perf [fuse] [lag]    # 23 blocks, 25 windows of 276x276: trunk ms, layer-by-layer vs fused
     python tools/try_fused.py trace [fuse] [lag]   # clock64 stamps of CTA 0's first 64 tasks of RDB 2
+    python tools/try_fused.py fold                 # folded nearest-x2 upsample (csrc/ups_kernel.cuh): bit-identity + tail ms
 """
 import os
 import sys
@@ -86,8 +87,25 @@ def trace(fuse, lag):
     return 0
 
 
+def fold():
+    """Folded nearest-x2 upsample (csrc/ups_kernel.cuh, option tail_fold_upsample): same arithmetic as the product tail, so the
+    outputs must be bit-identical; `tail` of the timing line is what changes."""
+    for blocks, (H, W), tile in ((1, (300, 290), 256), (1, (300, 290), 128), (23, (1044, 1044), 256)):
+        tensors = net(blocks, 4)
+        img = np.random.default_rng(13).integers(0, 256, (H, W, 3), dtype=np.uint8)
+        try:
+            (u8, f), _ = run(tensors, blocks, img, tile, want_float=True, reps=2)
+            (u8_d, f_d), _ = run(tensors, blocks, img, tile, want_float=True, reps=2, tail_fold_upsample=1)
+        except Exception as e:  # noqa: BLE001
+            print(f"  {H}x{W} tile {tile} blocks {blocks}: FAILED {e}", flush=True)
+            return 1
+        print(f"  {H}x{W} tile {tile} blocks {blocks}: identical u8 {bool(np.array_equal(u8, u8_d))}  identical float {bool(np.array_equal(f, f_d))}  "
+              f"max float diff {float(np.abs(f - f_d).max()):.3e}", flush=True)
+    return 0
+
+
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "check"
     fuse = int(sys.argv[2]) if len(sys.argv) > 2 else 4
     lag = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-    sys.exit({"check": check, "perf": lambda: perf(fuse, lag), "trace": lambda: trace(fuse, lag)}[mode]())
+    sys.exit({"check": check, "perf": lambda: perf(fuse, lag), "trace": lambda: trace(fuse, lag), "fold": fold}[mode]())
