@@ -192,7 +192,7 @@ def test_scene_plan_properties():
     from hypothesis import given, settings, strategies as st
     scene = importlib.import_module("sentinel2-super-resolution-poc_b200.scene")
 
-    @settings(max_examples=120, deadline=None)
+    @settings(max_examples=120, deadline=None, derandomize=True)
     @given(st.integers(20, 700), st.integers(20, 700), st.sampled_from([16, 32, 64, 100, 256]), st.integers(1, 8))
     def check(H, W, tile, world):
         plans = [scene.ScenePlan(H, W, tile, world, r) for r in range(world)]
