@@ -327,6 +327,29 @@ def run_ours(args):
         e2e = {"value": out_mpix / (e_ms / 1e3), "unit": "Mpix/s", "h2d_bytes_per_step": int(src.nbytes), "d2h_bytes_per_step": int(src.nbytes),
                "ms_per_step": e_ms, "api": "_enhance_for_crops(np.ndarray)"}
 
+    # The literal reference call sequence with numpy arrays (wow_sr.py:94-110): enhance(host) -> cvtColor -> _enhance_for_crops(host).
+    # Two host round trips through pageable memory; reported next to `e2e.value` (which keeps the SR image on the GPU between the
+    # two stages, like apply_wow_sr does), never instead of it.  Guarded: a failure here must not cost the bench line.
+    if e2e is not None and tile > 0 and world == 1:
+        try:
+            import cv2
+
+            def step_dropin():
+                sr = up.enhance(host_img)
+                rgb = cv2.cvtColor(sr, cv2.COLOR_BGR2RGB)
+                return ws.app.wow_sr._enhance_for_crops(rgb) if wl["post"] else rgb
+
+            step_dropin()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(2):
+                step_dropin()
+            d_ms = (time.perf_counter() - t0) / 2 * 1e3
+            e2e["dropin_two_calls"] = {"value": out_mpix / (d_ms / 1e3), "unit": "Mpix/s", "ms_per_step": d_ms,
+                                       "api": "RealESRGAN.enhance(ndarray) -> cv2.cvtColor -> _enhance_for_crops(ndarray), pageable host arrays"}
+        except Exception as e:  # noqa: BLE001
+            e2e["dropin_two_calls"] = {"error": str(e)[:200]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
