@@ -207,10 +207,14 @@ def run_ours(args):
     H, W, tile = wl["H"], wl["W"], wl["tile"]
     blocks = 23
     sd = R.random_init_state_dict(0, blocks)
-    up = ws.app.cnn_super_resolution.RealESRGAN(scale=4, device=f"cuda:{local}", tile_size=max(tile, 1), state_dict=sd, precision=args.precision)
-    for kv in args.opt:
-        k, v = kv.split("=")
-        up._h.set_option(k, int(v))
+    handle = None
+    if args.opt:  # options first: some (trunk_fuse, trunk_dataflow, tc_chunk32) decide how the weights are packed at load time
+        handle = ws.Handle(local)
+        for kv in args.opt:
+            k, v = kv.split("=")
+            handle.set_option(k, int(v))
+    up = ws.app.cnn_super_resolution.RealESRGAN(scale=4, device=f"cuda:{local}", tile_size=max(tile, 1), state_dict=sd, precision=args.precision,
+                                                handle=handle)
     params = ws._lib.post_params("wow")
     backend = scene.GpuBackend(up, params)
 

@@ -31,5 +31,8 @@ if grep -q "exit 0" $O/r2_fused_check.txt; then
       --csv --log-file $O/r2_dram_fuse$fuse.csv python tools/try_fused_ncu.py $fuse > $O/r2_dram_fuse$fuse.log 2>&1
   done
   python tools/dram_compare.py $O/r2_dram_fuse0.csv $O/r2_dram_fuse4.csv > $O/r2_dram_compare.txt 2>&1
+  # the headline workload under the power cap, both paths back to back (a bench line produced with --opt is an experiment, not a result)
+  timeout 240 python bench.py --no-cpu > $O/r2_bench_cfg2_base.json 2> $O/r2_bench_cfg2_base.err
+  timeout 240 python bench.py --no-cpu --opt trunk_fuse=4 > $O/r2_bench_cfg2_fuse4.json 2> $O/r2_bench_cfg2_fuse4.err
 fi
 echo done
