@@ -115,3 +115,31 @@ def test_apply_farm_sr_files(ws, tmp_path, monkeypatch):
                                                            strength=1.2, radius=1.5))
     assert np.array_equal(got, step)
     cnn.clear_model_cache()
+
+
+def test_geotiff_branches_of_read_and_write_image(ws, tmp_path, monkeypatch):
+    """rasterio is absent from this image: run the GeoTIFF branches of the IO glue (wow_sr.py:57-79, :126-164) against an
+    in-memory stand-in (tests/fake_rasterio.py) so they are exercised before production."""
+    from tests import fake_rasterio as FR
+    FR.install(monkeypatch)
+    wow = ws.app.wow_sr
+    rng = np.random.default_rng(3)
+    bands = [rng.integers(0, 9000, (12, 17)).astype(np.uint16) for _ in range(4)]          # 4-band Sentinel-2 style raster
+    FR.put(tmp_path / "s2.tif", bands)
+    img, transform, crs = wow.read_image(tmp_path / "s2.tif")
+    assert img.shape == (12, 17, 3) and img.dtype == np.uint16 and crs == "EPSG:32636"
+    assert all(np.array_equal(img[..., i], bands[i]) for i in range(3))                      # bands 1-3 as R, G, B
+    FR.put(tmp_path / "gray.tiff", bands[:1])
+    g, _, _ = wow.read_image(tmp_path / "gray.tiff")
+    assert g.shape == (12, 17, 3) and all(np.array_equal(g[..., i], bands[0]) for i in range(3))   # one band replicated
+    rgb = rng.integers(0, 256, (48, 68, 3), dtype=np.uint8)
+    out = wow.write_image(rgb, tmp_path / "o" / "scene_wow.tif", transform, crs, 4)
+    assert out == tmp_path / "o" / "scene_wow.tif" and out.exists() and (tmp_path / "o" / "scene_wow.png").exists()
+    rec = FR.STORE[str(out)]
+    assert rec["transform"] == FR.Affine(2.5, 0.0, 5e5, 0.0, -2.5, 4e6) and rec["crs"] == crs      # pixel size / scale (:131-138)
+    assert rec["kw"]["driver"] == "GTiff" and rec["kw"]["compress"] == "lzw" and rec["kw"]["dtype"] == "uint8"
+    assert all(np.array_equal(rec["bands"][i], rgb[..., i]) for i in range(3))
+    import cv2
+    assert np.array_equal(cv2.imread(str(tmp_path / "o" / "scene_wow.png"))[:, :, ::-1], rgb)
+    # without georeferencing only the PNG is written and returned
+    assert wow.write_image(rgb, tmp_path / "p" / "plain.tif", None, None, 4) == tmp_path / "p" / "plain.png"
