@@ -91,3 +91,16 @@ def test_split_trunk_representation_bound():
     # (acc + 5*hi) * 0.2f reproduces hi to fp32 rounding: 5 * fl(0.2) = 1 + 1.5e-8
     back = (5.0 * hi) * torch.tensor(0.2, dtype=torch.float32)
     assert float(((back - hi).abs() / hi.abs().clamp_min(1e-30)).max()) <= 2.0 ** -23
+
+
+def test_product_parameter_container_draws_the_reference_init_stream(ws):
+    """bench.py draws its seed-0 weights through the package's own RRDBNet container (nothing under oracle/ in the measured
+    arm): same construction order as the reference class, hence the same RNG stream — pinned by the reference's checksums."""
+    g = np.load(os.path.join(GOLD, "init_checksums.npz"))
+    torch.manual_seed(0)
+    sd = ws.app.cnn_super_resolution.RRDBNet(3, 3, 64, 23, 32, 4).state_dict()
+    assert len(sd) == 702 and list(sd) == list(R.random_init_state_dict(0, 23))
+    for n, s, a in zip(g["names"], g["sums"], g["abssums"]):
+        t = sd[str(n)].double()
+        assert float(t.sum()) == pytest.approx(float(s), abs=1e-9)
+        assert float(t.abs().sum()) == pytest.approx(float(a), abs=1e-9)
