@@ -74,7 +74,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:  # noqa: BLE001
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, pw = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
@@ -85,11 +85,19 @@ class ClockSampler:
                 mx = float(f[1])
             except ValueError:
                 continue
+            try:
+                pw.append(float(f[2]))
+            except ValueError:
+                pass
             for n, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        pw.sort()
+        # power_w: median board power during the timed region — every full-size run is power-capped, so energy per step
+        # (power x ms_per_step) is the quantity to compare between kernel variants
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "power_w": pw[len(pw) // 2] if pw else None}
 
 
 def make_lr_image(H, W, seed=1):

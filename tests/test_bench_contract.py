@@ -45,3 +45,13 @@ def test_workloads_name_the_baseline_configs():
     assert bench.FLOP_PER_LR_PX == 3456 + 69 * 479232 + 73728 + 294912 + 2 * 1179648 + 55296
     with pytest.raises(SystemExit):
         bench.workload("nope", 1)
+
+
+def test_clock_sampler_parses_nvidia_smi_lines():
+    c = bench.ClockSampler(0)
+    c.proc = type("P", (), {"terminate": lambda s: None, "wait": lambda s, timeout=None: None, "kill": lambda s: None})()
+    c.lines = ["1372, 1965, 998.21, Not Active, Not Active, Not Active, Active", "1380, 1965, 1001.5, Not Active, Not Active, Not Active, Active",
+               "1365, 1965, [N/A], Not Active, Active, Not Active, Not Active", "garbage"]
+    got = c.stop()
+    assert got == {"sm_mhz": 1372.0, "sm_max_mhz": 1965.0, "reasons": ["hw_thermal_slowdown", "sw_power_cap"], "samples": 3, "power_w": 1001.5}
+    assert bench.ClockSampler(0).stop()["reasons"] == ["nvidia-smi unavailable"]
