@@ -298,7 +298,7 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
   size_t wtotal = L.chunk_bytes * L.n_chunks + id_bytes;
   size_t chunk_bytes = L.chunk_bytes;
   P.chunk_ch = 64;
-  P.astage = TC_ASTAGE;
+  P.astage = io.in_ups ? 2 * TC_UPS_ROWB : TC_ASTAGE;  // folded-upsample stages: two 1024-aligned 132-pixel rows
   if (wtotal + 2 * (size_t)TC_ASTAGE + SMEM_SLACK <= SMEM_LIMIT && L.n_chunks <= TC_MAX_WBUF &&
       !wowsr_opt(ctx, "tc_force_stream", 0)) {
     P.w_resident = 1;

@@ -719,8 +719,11 @@ __device__ __forceinline__ void issue_chunk(const ConvParams& P, IssueState& S, 
 
 // The MMA issuer role for all tiles of this CTA.
 // UPS (ups_kernel.cuh): the stage rows hold the x-replicated source starting one pixel early (132 pixels), so the A
-// descriptors start 128 B into the row and the second row of a stage is TC_UPS_ROWB further.
-constexpr int TC_UPS_ROWB = 132 * 128;
+// descriptors start 128 B into the row and the second row of a stage is TC_UPS_ROWB further.  Each row is its own TMA box;
+// the pitch is rounded up to 1024 B so that every box lands on a swizzle-atom boundary (no reliance on how the TMA unit
+// swizzles a destination that is only 128-byte aligned).
+constexpr int TC_UPS_ROWB = 17 * 1024;  // >= 132 * 128
+constexpr int TC_UPS_BOXB = 132 * 128;  // bytes one box delivers
 template <int N, int R, bool SINGLE, bool UPS = false>
 __device__ __forceinline__ void mma_issuer(const ConvParams& P, TcSmemCtl* ctl, bool leader, bool committer, uint32_t a_smem,
                                            uint32_t w_smem, uint32_t id_smem, uint32_t tmem_base, int n_my) {

@@ -74,7 +74,7 @@ conv3x3_tc_ups_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_c
         if (!ptx::mbar_wait_wd(ptx::smem_u32(&ctl->a_empty[stage]), aphase ^ 1, wd)) tc_fail(P, 12);
         if (leader) {
           const uint32_t full = ptx::smem_u32(&ctl->a_full[stage]);
-          ptx::mbar_arrive_expect_tx(full, 2 * TC_UPS_ROWB);
+          ptx::mbar_arrive_expect_tx(full, 2 * TC_UPS_BOXB);
 #pragma unroll
           for (int half = 0; half < 2; half++) {
             const int row_up = tc.v0 - 1 + 2 * sp + half;  // row of the upsampled image (or column, for vertical tiles)

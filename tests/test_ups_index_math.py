@@ -2,7 +2,7 @@
 
 The kernel never sees an upsampled tensor: per stage row it loads the box (rep = 0..1, source pixels xs0 .. xs0 + 65) of source row
 ``row_up >> 1`` with ``xs0 = (u0 >> 1) - 1`` (out-of-bounds elements zero filled), which lands in shared memory in pixel order
-``2 * (xs - xs0) + rep``; the MMA of output pixel ``m`` and run-axis tap ``kx`` reads stage pixel ``1 + m + kx`` (descriptor start
+``2 * (xs - xs0) + rep`` (each row its own box on a 1024-byte boundary); the MMA of output pixel ``m`` and run-axis tap ``kx`` reads stage pixel ``1 + m + kx`` (descriptor start
 +128 B, tap shift kx * 128 B).  This test replays exactly that addressing for every tile of small images and compares with
 ``conv3x3(nearest_x2(src))`` with zero padding — the reference's ``conv(F.interpolate(x, scale_factor=2, mode="nearest"))``
 (cnn_super_resolution.py:150-153)."""

@@ -7,8 +7,8 @@
 // descriptors walk (SWIZZLE_128B, checked here through the same address-bit swizzle the kernel relies on).  The y replication
 // needs no map support: the producer issues one load per stage row with row >> 1.
 // Prints: the CUresult of cuTensorMapEncodeTiled, whether the loaded tile equals the replicated source (incl. the zero fill
-// left of x = 0 and right of x = W - 1), and the same for a destination that is only 128-byte (not 1024-byte) aligned, which is
-// what the second row of a two-row stage would be.
+// left of x = 0 and right of x = W - 1), the same for the second-row destination the kernel uses (+17408, 1024-byte aligned), and —
+// for information — for destinations that are only 128-byte aligned (+16896, +128).
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I sentinel2-super-resolution-poc_b200/csrc \
 //        tools/tma_stride0_probe.cu -o build/tma_stride0_probe
 #include <cudaTypedefs.h>
@@ -87,7 +87,7 @@ int main() {
   const int smem = 64 * 1024;
   cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   std::vector<uint16_t> out((size_t)BOX_W * 2 * C);
-  const int cases[][3] = {{-1, 1, 0}, {W - 60, 2, 0}, {40, 0, 16896}, {40, 0, 128}};  // {first source x, row, destination offset}
+  const int cases[][3] = {{-1, 1, 0}, {W - 60, 2, 0}, {40, 0, 17408}, {40, 0, 16896}, {40, 0, 128}};  // {first source x, row, destination offset}
   for (auto& cs : cases) {
     const int xs0 = cs[0], row = cs[1];
     probe_kernel<<<1, 128, smem>>>(tm, xs0, row, (uint32_t)cs[2], d_out);
