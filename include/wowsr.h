@@ -198,16 +198,6 @@ int32_t wowsr_get_timing(const wowsr_ctx* ctx, float* ms, int32_t cap);
  * launch selected with wowsr_set_option("tc_trace_layer", k) (k = 1-based launch index). Returns count. */
 int32_t wowsr_debug_trace(wowsr_ctx* ctx, int64_t* out, int32_t cap);
 
-/* Debug / test introspection of an EXPERIMENTAL path (option trunk_fuse, csrc/sched_plan.h — round-2 work in progress,
- * not on the product path): the host-built task list of the fused-tail launch that runs convs `first_conv`..5 (1-based,
- * 1..4) of one ResidualDenseBlock (cnn_super_resolution.py:85-91) over `n_win` windows of h x w.  Pure host function.
- * Each task is 8 uint16: {k | vert << 8, window, u0, v0, dep_band0, dep_bands, pub_band0, pub_bands}; info[8] receives
- * {lag, n_bands, publishing tiles per band, strip_x0, band_rows, fused convs, epilogue warps, 0}.  lag = 0: automatic
- * (legal minimum + latency slack), lag = -1: the legal minimum itself.
- * Returns the task count (tasks are written when cap is large enough) or < 0. */
-int32_t wowsr_debug_fused_schedule(int32_t h, int32_t w, int32_t n_win, int32_t first_conv, int32_t lag,
-                                   uint16_t* tasks, int32_t cap, int32_t* info);
-
 /* ------------------------------------------------------------------------------------------ */
 /* EDSR-baseline x4 "farm SR" variant (super_resolution.py:92-124,196: cv2.dnn_superres          */
 /* DnnSuperResImpl.upsample with EDSR_x4.pb — third-party, parity unpinned)       */

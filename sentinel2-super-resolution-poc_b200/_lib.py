@@ -70,8 +70,6 @@ _SIGS = {
                                      C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "wowsr_get_timing": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float), C.c_int32]),
     "wowsr_debug_trace": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
-    "wowsr_debug_fused_schedule": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
-                                               C.POINTER(C.c_int32)]),
     "wowsr_load_edsr": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.POINTER(C.c_void_p), C.c_int32, C.c_int32]),
     "wowsr_edsr_upsample_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
 }
@@ -100,6 +98,19 @@ def exported_symbols():
 
 class WowsrError(RuntimeError):
     pass
+
+
+def _locked(fn):
+    """Serialises a Handle method on the handle's lock: a wowsr_ctx keeps its scratch (histograms, LUTs, staging buffers,
+    workspace) inside the context, and the server runs /api/wow, /api/sr and /api/pipeline jobs on concurrent worker threads
+    (main.py:519,607,670-675) that share the per-device default handle."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **kw):
+        with self.lock:
+            return fn(self, *a, **kw)
+    return wrapper
 
 
 class Handle:
@@ -134,6 +145,7 @@ class Handle:
             raise WowsrError(f"{what} failed ({rc}): {self._L.wowsr_last_error(self._h).decode()}")
 
     # -- misc ---------------------------------------------------------------------------------
+    @_locked
     def set_option(self, key: str, value: int):
         self._check(self._L.wowsr_set_option(self._h, key.encode(), int(value)), "set_option")
 
@@ -151,6 +163,7 @@ class Handle:
         return np.array(list(buf)[:max(n, 0)], dtype=np.int64).reshape(-1, 4)
 
     # -- post-process -------------------------------------------------------------------------
+    @_locked
     def post_process_host(self, img: np.ndarray, params: PostParams) -> np.ndarray:
         img = np.ascontiguousarray(img, dtype=np.uint8)
         if img.ndim != 3 or img.shape[2] != 3:
@@ -160,6 +173,7 @@ class Handle:
                                                     out.ctypes.data), "post_process_host")
         return out
 
+    @_locked
     def post_process_dev(self, src_ptr, dst_ptr, H, W, params, stream=0, pitch=None):
         pitch = pitch or W * 3
         a = Image(src_ptr, pitch, W, H, 0, H)
@@ -167,14 +181,17 @@ class Handle:
         self._check(self._L.wowsr_post_process_dev(self._h, C.byref(a), C.byref(params), C.byref(b), C.c_void_p(stream)),
                     "post_process_dev")
 
+    @_locked
     def clahe_hist(self, image: Image, grid, prow0, prow1, hist_ptr, stream=0):
         self._check(self._L.wowsr_clahe_hist(self._h, C.byref(image), grid, prow0, prow1, C.c_void_p(hist_ptr), C.c_void_p(stream)),
                     "clahe_hist")
 
+    @_locked
     def clahe_luts(self, hist_ptr, grid, tw, th, clip, luts_ptr, stream=0):
         self._check(self._L.wowsr_clahe_luts(self._h, C.c_void_p(hist_ptr), grid, tw, th, float(clip), C.c_void_p(luts_ptr),
                                              C.c_void_p(stream)), "clahe_luts")
 
+    @_locked
     def post_apply(self, src: Image, luts_ptr, params, row0, row1, dst: Image, stream=0):
         self._check(self._L.wowsr_post_apply(self._h, C.byref(src), C.c_void_p(luts_ptr), C.byref(params), row0, row1, C.byref(dst),
                                              C.c_void_p(stream)), "post_apply")
@@ -190,6 +207,7 @@ class Handle:
                 a.lo[c], a.hi[c] = int(lo[c]), int(hi[c])
         return arr
 
+    @_locked
     def green_mask_host(self, img: np.ndarray, ranges) -> np.ndarray:
         img = np.ascontiguousarray(img, dtype=np.uint8)
         if img.ndim != 3 or img.shape[2] != 3:
@@ -200,6 +218,7 @@ class Handle:
                                                   out.ctypes.data), "green_mask_host")
         return out
 
+    @_locked
     def green_mask_dev(self, src_ptr, H, W, ranges, mask_ptr, stream=0, pitch=None, mask_pitch=None):
         a = Image(src_ptr, pitch or W * 3, W, H, 0, H)
         arr = self._hsv_ranges(ranges)
@@ -207,12 +226,14 @@ class Handle:
                                              C.c_void_p(stream)), "green_mask")
 
     # -- network ------------------------------------------------------------------------------
+    @_locked
     def load_rrdbnet(self, tensors, num_block, num_feat=64, num_grow=32, precision="bf16"):
         arrs = [np.ascontiguousarray(t, dtype=np.float32) for t in tensors]
         ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
         self._check(self._L.wowsr_load_rrdbnet(self._h, num_block, num_feat, num_grow, ptrs, len(arrs), PREC[precision]),
                     "load_rrdbnet")
 
+    @_locked
     def enhance_host(self, img: np.ndarray, tile_size: int, want_float=False):
         img = np.ascontiguousarray(img, dtype=np.uint8)
         H, W = img.shape[:2]
@@ -222,10 +243,12 @@ class Handle:
                                                outf.ctypes.data if want_float else None), "enhance_host")
         return (out, outf) if want_float else out
 
+    @_locked
     def enhance_dev(self, src_ptr, H, W, tile_size, dst_ptr, dst_f32_ptr=None, stream=0):
         self._check(self._L.wowsr_enhance_dev(self._h, C.c_void_p(src_ptr), H, W, tile_size, C.c_void_p(dst_ptr),
                                               C.c_void_p(dst_f32_ptr) if dst_f32_ptr else None, C.c_void_p(stream)), "enhance_dev")
 
+    @_locked
     def forward_windows(self, src_ptr, H, W, pitch, windows, dst_ptr, dst_pitch, dst_f32_ptr=None, dst_f32_pitch=0, stream=0):
         arr = (Window * len(windows))(*windows)
         self._check(self._L.wowsr_rrdbnet_forward_windows(self._h, C.c_void_p(src_ptr), H, W, pitch, arr, len(windows),
@@ -233,6 +256,7 @@ class Handle:
                                                           C.c_void_p(dst_f32_ptr) if dst_f32_ptr else None, dst_f32_pitch,
                                                           C.c_void_p(stream)), "rrdbnet_forward_windows")
 
+    @_locked
     def conv3x3_host(self, x, weight, bias, act=0, precision="bf16"):
         x = np.ascontiguousarray(x, dtype=np.float32)
         weight = np.ascontiguousarray(weight, dtype=np.float32)
@@ -244,12 +268,14 @@ class Handle:
                                                int(act), PREC[precision], out.ctypes.data), "conv3x3_host")
         return out
 
+    @_locked
     def load_edsr(self, tensors, num_block=16, num_feat=64, res_scale=1.0, precision="bf16"):
         arrs = [np.ascontiguousarray(t, dtype=np.float32) for t in tensors]
         ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
         self._check(self._L.wowsr_load_edsr(self._h, num_block, num_feat, float(res_scale), ptrs, len(arrs), PREC[precision]),
                     "load_edsr")
 
+    @_locked
     def edsr_upsample_host(self, img: np.ndarray, want_float=False):
         img = np.ascontiguousarray(img, dtype=np.uint8)
         H, W = img.shape[:2]
@@ -286,19 +312,6 @@ def gaussian_taps(sigma):
     return list(buf)[:n]
 
 
-def fused_schedule(h, w, n_win, first_conv=4, lag=0):
-    """Task list of the experimental fused-tail launch (csrc/sched_plan.h) as an (n, 8) uint16 array + its info dict."""
-    L = lib()
-    info = (C.c_int32 * 8)()
-    n = L.wowsr_debug_fused_schedule(h, w, n_win, first_conv, lag, None, 0, info)
-    if n < 0:
-        raise ValueError(f"no schedule for {n_win} windows of {h}x{w} (first conv {first_conv}, lag {lag})")
-    arr = np.empty((n, 8), dtype=np.uint16)
-    L.wowsr_debug_fused_schedule(h, w, n_win, first_conv, lag, arr.ctypes.data, n, info)
-    keys = ("lag", "n_bands", "band_target_tiles", "strip_x0", "band_rows", "n_layers", "epi_warps")
-    return arr, dict(zip(keys, list(info)))
-
-
 _TABLES = {0: ("gam", np.uint16, 256), 1: ("cbrt", np.uint16, 3072), 2: ("lab_y", np.uint16, 256),
            3: ("lab_ify", np.uint16, 256), 4: ("invgam", np.uint8, 4096), 5: ("sdiv", np.uint32, 256),
            6: ("hdiv", np.uint32, 256)}
@@ -326,11 +339,13 @@ def post_params(kind="wow", **over) -> PostParams:
 _handles = {}
 
 
+_handles_lock = threading.Lock()
+
+
 def default_handle(device: int = 0) -> Handle:
-    with _lock:
+    """The process-wide handle of `device` (created once, inside the critical section)."""
+    with _handles_lock:
         h = _handles.get(device)
-    if h is None:
-        h = Handle(device)
-        with _lock:
-            _handles[device] = h
+        if h is None:
+            h = _handles[device] = Handle(device)
     return h

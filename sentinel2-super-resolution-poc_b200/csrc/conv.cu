@@ -9,8 +9,6 @@
 
 #include "common.h"
 #include "conv_kernels.cuh"
-#include "trunk_kernel.cuh"
-#include "sched_kernel.cuh"
 #include "ups_kernel.cuh"
 
 namespace {
@@ -24,7 +22,7 @@ struct LayerW {
   bool fp16 = false;  // operand type of this layer (input activations and weights)
   uint8_t* wpack = nullptr;
   uint8_t* wpack_v = nullptr;  // taps transposed, for vertical tiles
-  uint8_t* wpack32 = nullptr;  // same as [chunk of 32 ch][kx][j][co][32ch] (SWIZZLE_64B rows): layers whose weights are streamed
+  uint8_t* wpack32 = nullptr;  // same as [chunk of 32 ch][kx][j][co][32ch] (SWIZZLE_64B rows): streamed layers under option tc_chunk32
   uint8_t* wpack32_v = nullptr;
   size_t chunk_bytes32 = 0;
   float* wsimple = nullptr;
@@ -42,10 +40,6 @@ struct ConvNet {
   float* first_b = nullptr;
   std::vector<LayerW> layers;
   DevBuf dense0, dense1, feat, trunk, rrdb, lo, up1, hra, hrb, wins, winxy, err;
-  DevBuf trunk_tab, trunk_ctr;  // experimental dataflow trunk (trunk_kernel.cuh): weight table, dependency counters
-  DevBuf sched_tasks;           // experimental fused tail (sched_kernel.cuh): task list of the current batch shape
-  int sched_key[5] = {0, 0, 0, 0, 0};  // (n_win, h, w, k_first, lag) the list was built for
-  int sched_n_tasks = 0, sched_n_bands = 0, sched_target = 0;
 };
 
 void wowsr_net_free(ConvNet* n) {
@@ -60,7 +54,7 @@ void wowsr_net_free(ConvNet* n) {
   }
   if (n->first_w) cudaFree(n->first_w);
   if (n->first_b) cudaFree(n->first_b);
-  DevBuf* bufs[] = {&n->sched_tasks, &n->trunk_tab, &n->trunk_ctr, &n->dense0, &n->dense1, &n->feat, &n->trunk, &n->rrdb, &n->lo, &n->up1, &n->hra, &n->hrb, &n->wins, &n->winxy, &n->err};
+  DevBuf* bufs[] = {&n->dense0, &n->dense1, &n->feat, &n->trunk, &n->rrdb, &n->lo, &n->up1, &n->hra, &n->hrb, &n->wins, &n->winxy, &n->err};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   delete n;
@@ -130,8 +124,7 @@ int upload_layer(wowsr_ctx* ctx, LayerW& L, const float* w, const float* b, int 
   // double buffer (run_conv picks the mode with the same test)
   // Measured (profiles/r01_epilogue_breakdown.txt, exp9): -4 % cycles per rdb.conv5 tile but no time gain under the
   // power cap, so the mode is opt-in (option tc_chunk32=1 before loading the network).
-  if ((wowsr_opt(ctx, "tc_chunk32", 0) && L.chunk_bytes * L.n_chunks + 2 * (size_t)TC_ASTAGE + SMEM_SLACK > SMEM_LIMIT) ||
-      wowsr_opt(ctx, "trunk_dataflow", 0) || wowsr_opt(ctx, "trunk_fuse", 0)) {  // the experimental trunk kernels stream every layer in 32-channel chunks
+  if (wowsr_opt(ctx, "tc_chunk32", 0) && L.chunk_bytes * L.n_chunks + 2 * (size_t)TC_ASTAGE + SMEM_SLACK > SMEM_LIMIT) {
     L.chunk_bytes32 = (size_t)3 * 3 * N * 64;
     const int nc32 = cin / 32;
     std::vector<uint8_t> p32(L.chunk_bytes32 * nc32, 0), p32v(L.chunk_bytes32 * nc32, 0);
@@ -220,7 +213,7 @@ int make_tmap(wowsr_ctx* ctx, CUtensorMap* m, const void* base, int C, int W, in
   return 0;
 }
 
-// EXPERIMENTAL (ups_kernel.cuh): 5-D map of the x-upsampled view of an NHWC buffer [Nw][Hs][Ws][C]: dims (C, rep = 2 with a
+// Folded upsample (ups_kernel.cuh): 5-D map of the x-upsampled view of an NHWC buffer [Nw][Hs][Ws][C]: dims (C, rep = 2 with a
 // ZERO stride, Ws, Hs, Nw), box (64 ch, 2, 66 source pixels, 1 row, 1 window) = 132 upsampled pixels.  `transposed`: the run
 // axis (the replicated one) walks y, for the vertical tiles.  Whether the driver accepts a zero stride is what
 // tools/tma_stride0_probe.cu measures; a rejection surfaces here as an error, never as a silent fallback.
@@ -262,7 +255,7 @@ struct LayerIO {
   void* out_t = nullptr;
   int out_stride = 0, out_choff = 0, out_rep = 1;
   int out_ps = 0;
-  int in_ups = 0;  // experimental: `in` is at HALF the layer resolution, the nearest-x2 upsample is folded into the tensor maps
+  int in_ups = 0;  // `in` is at HALF the layer resolution, the nearest-x2 upsample is folded into the tensor maps
   float final_scale = 255.0f;
   float final_add[3] = {0.0f, 0.0f, 0.0f};
   int final_round = 0;
@@ -408,7 +401,7 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
     }
   }
   size_t smem = (size_t)P.n_stage * P.astage + (size_t)P.n_wbuf * chunk_bytes + id_bytes + SMEM_SLACK;
-  if (io.in_ups) {  // experimental folded-upsample kernel (ups_kernel.cuh): plain epilogue only
+  if (io.in_ups) {  // folded-upsample kernel (ups_kernel.cuh): plain epilogue only
     if (P.final || P.res1 || P.res2 || P.out_f32_a || P.out_f32_b || P.lo_in || P.lo_out || P.out_rep != 1 || P.out_ps || !P.out_t)
       return wowsr_fail(ctx, WOWSR_ERR_UNSUPPORTED, "folded upsample: plain epilogue only");
     WCUDA(ctx, cudaFuncSetAttribute(conv3x3_tc_ups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
@@ -450,151 +443,6 @@ int check_err_flag(wowsr_ctx* ctx, ConvNet* net, cudaStream_t st) {
   if (flag) {
     cudaMemsetAsync(net->err.p, 0, 4, st);
     return wowsr_fail(ctx, WOWSR_ERR_CUDA, "tensor-core conv kernel watchdog tripped (code %d)", flag);
-  }
-  return 0;
-}
-
-// EXPERIMENTAL (option trunk_dataflow=1, see trunk_kernel.cuh): the residual trunk of one batch as one persistent launch
-// per group of `trunk_group` windows.  Expects conv_first's outputs in dense0 / rrdb; leaves the trunk output where the
-// layer-by-layer loop would (hi in dense[(3 * num_block) & 1], fp32 in rrdb).
-int run_trunk_dataflow(wowsr_ctx* ctx, ConvNet* net, int nb, int h, int w, const F32Layout& fl, bool body16, bool tail16,
-                       cudaStream_t st) {
-  const int n_rdb = 3 * net->num_block;
-  for (int i = 0; i < n_rdb * 5; i++)
-    if (!net->layers[i].wpack32) return wowsr_fail(ctx, WOWSR_ERR_STATE, "set option trunk_dataflow=1 before loading the network");
-  if (!net->trunk_tab.p) {
-    std::vector<TrunkLayerW> tab(n_rdb * 5);
-    for (int i = 0; i < n_rdb * 5; i++) tab[i] = TrunkLayerW{net->layers[i].wpack32, net->layers[i].wpack32_v, net->layers[i].bias};
-    if (int e = wowsr_ensure(ctx, net->trunk_tab, tab.size() * sizeof(TrunkLayerW))) return e;
-    WCUDA(ctx, cudaMemcpy(net->trunk_tab.p, tab.data(), tab.size() * sizeof(TrunkLayerW), cudaMemcpyHostToDevice));
-  }
-  int G = (int)wowsr_opt(ctx, "trunk_group", 2);
-  if (G < 1) G = 1;
-  if (int e = wowsr_ensure(ctx, net->trunk_ctr, (size_t)n_rdb * 5 * G * 4)) return e;
-  TrunkParams T;
-  memset(&T, 0, sizeof T);
-  T.h = h; T.w = w; T.n_rdb = n_rdb;
-  T.fp16 = body16; T.last_fp16 = tail16;
-  T.idesc_base = make_idesc_f16(128, 0, body16);
-  T.f32 = fl;
-  T.strip_x0 = fl.x0;  // strip columns (blocked along y in the fp32 / lo buffers) are covered by vertical tiles
-  for (int kind = 0; kind < 2; kind++) {
-    const int R = kind ? 4 : 8;
-    TrunkKind& K = T.kind[kind];
-    K.tiles_x = (T.strip_x0 + TC_RUN - 1) / TC_RUN;
-    K.tiles_y = (h + R - 1) / R;
-    K.n_h = K.tiles_x * K.tiles_y;
-    K.v_runs = fl.rem ? (h + TC_RUN - 1) / TC_RUN : 0;
-    K.v_rows = fl.rem ? (fl.rem + R - 1) / R : 0;
-    K.n_v = K.v_runs * K.v_rows;
-    K.n = K.n_h + K.n_v;
-  }
-  T.dense[0] = (uint16_t*)net->dense0.p; T.dense[1] = (uint16_t*)net->dense1.p;
-  T.lo = (uint16_t*)net->lo.p; T.rrdb = (float*)net->rrdb.p;
-  T.layers = (const TrunkLayerW*)net->trunk_tab.p;
-  T.counters = (unsigned int*)net->trunk_ctr.p;
-  T.err_flag = (int*)net->err.p;
-  T.n_stage = (int)((SMEM_LIMIT - SMEM_SLACK - 2 * (size_t)TRUNK_WBUF_BYTES - 8192) / TC_ASTAGE32);
-  if (T.n_stage > TC_MAX_STAGES) T.n_stage = TC_MAX_STAGES;
-  const size_t smem = (size_t)T.n_stage * TC_ASTAGE32 + 2 * (size_t)TRUNK_WBUF_BYTES + 8192 + SMEM_SLACK;
-  CUtensorMap tm[2][2];
-  for (int b = 0; b < 2; b++)
-    for (int v = 0; v < 2; v++)
-      if (int e = make_tmap(ctx, &tm[b][v], b ? net->dense1.p : net->dense0.p, 192, w, h, nb, body16, v == 1, true)) return e;
-  WCUDA(ctx, cudaFuncSetAttribute(rdb_trunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
-  for (int g0 = 0; g0 < nb; g0 += G) {
-    T.win0 = g0;
-    T.G = std::min(G, nb - g0);
-    const long long n_tasks = (long long)n_rdb * T.G * (4 * T.kind[0].n + T.kind[1].n);
-    const int grid = (int)std::min<long long>(ctx->sm_count, n_tasks);  // every CTA must be resident: tasks wait on each other
-    WCUDA(ctx, cudaMemsetAsync(net->trunk_ctr.p, 0, (size_t)n_rdb * 5 * G * 4, st));
-    rdb_trunk_kernel<<<grid, TC_THREADS, smem, st>>>(tm[0][0], tm[0][1], tm[1][0], tm[1][1], T);
-    WLAUNCH_CHECK(ctx);
-    if (wowsr_opt(ctx, "trunk_debug", 0)) {  // bring-up aid: published-warp counters per (rdb, layer, window) after the launch
-      std::vector<unsigned int> c((size_t)n_rdb * 5 * G);
-      cudaError_t ce = cudaStreamSynchronize(st);
-      cudaMemcpy(c.data(), net->trunk_ctr.p, c.size() * 4, cudaMemcpyDeviceToHost);
-      fprintf(stderr, "[trunk_debug] group %d: sync=%s grid=%d tasks=%lld n0=%d n1=%d targets %d / %d; counters:", g0,
-              cudaGetErrorString(ce), grid, n_tasks, T.kind[0].n, T.kind[1].n, T.kind[0].n * TC_EPI_WARPS, T.kind[1].n * TC_EPI_WARPS);
-      for (size_t i = 0; i < c.size() && i < 40; i++) fprintf(stderr, " %u", c[i]);
-      fprintf(stderr, "\n");
-    }
-  }
-  return 0;
-}
-
-// EXPERIMENTAL (option trunk_fuse = f, 1-based first fused conv, see sched_kernel.cuh): convs f..5 of RDB `rdb` over the whole
-// batch as one persistent launch that follows the skewed task list of sched_plan.h.  The caller has run convs 1..f-1 of this
-// RDB layer by layer; the launch leaves its outputs where the layer-by-layer convs would.
-int run_rdb_fused(wowsr_ctx* ctx, ConvNet* net, int rdb, int nb, int h, int w, const F32Layout& fl, bool body16, bool tail16,
-                  const CUtensorMap (&tm)[2][2], cudaStream_t st) {
-  const int n_rdb = 3 * net->num_block;
-  const int k_first = (int)wowsr_opt(ctx, "trunk_fuse", 4) - 1;
-  const int lag = (int)wowsr_opt(ctx, "trunk_lag", 0);  // 0: automatic (legal minimum for this window shape + latency slack)
-  if (k_first < 0 || k_first > 3) return wowsr_fail(ctx, WOWSR_ERR_ARG, "trunk_fuse must be 1..4 (first fused conv, 1-based)");
-  if (!net->trunk_tab.p) {
-    for (int i = 0; i < n_rdb * 5; i++)
-      if (!net->layers[i].wpack32) return wowsr_fail(ctx, WOWSR_ERR_STATE, "set option trunk_fuse before loading the network");
-    std::vector<TrunkLayerW> tab(n_rdb * 5);
-    for (int i = 0; i < n_rdb * 5; i++) tab[i] = TrunkLayerW{net->layers[i].wpack32, net->layers[i].wpack32_v, net->layers[i].bias};
-    if (int e = wowsr_ensure(ctx, net->trunk_tab, tab.size() * sizeof(TrunkLayerW))) return e;
-    WCUDA(ctx, cudaMemcpy(net->trunk_tab.p, tab.data(), tab.size() * sizeof(TrunkLayerW), cudaMemcpyHostToDevice));
-  }
-  const int key[5] = {nb, h, w, k_first, lag};
-  if (memcmp(key, net->sched_key, sizeof key) != 0 || !net->sched_tasks.p) {  // (re)build the task list for this batch shape
-    SchedPlan P;
-    if (!sched_build(P, h, w, nb, k_first, lag) && !sched_build(P, h, w, nb, k_first, 0, lag > 48 ? lag : 48, 0))
-      return wowsr_fail(ctx, WOWSR_ERR_UNSUPPORTED, "no fused-tail schedule for %d windows of %dx%d", nb, h, w);
-    if (P.strip_x0 != fl.x0) return wowsr_fail(ctx, WOWSR_ERR_STATE, "schedule and trunk layout disagree on the strip (%d vs %d)", P.strip_x0, fl.x0);
-    if (int e = wowsr_ensure(ctx, net->sched_tasks, P.tasks.size() * sizeof(SchedTask))) return e;
-    WCUDA(ctx, cudaMemcpyAsync(net->sched_tasks.p, P.tasks.data(), P.tasks.size() * sizeof(SchedTask), cudaMemcpyHostToDevice, st));
-    WCUDA(ctx, cudaStreamSynchronize(st));  // P goes out of scope
-    memcpy(net->sched_key, key, sizeof key);
-    net->sched_n_tasks = (int)P.tasks.size();
-    net->sched_n_bands = P.n_bands;
-    net->sched_target = P.band_target_tiles * TC_EPI_WARPS;
-  }
-  const size_t ctr_bytes = (size_t)(4 - k_first) * nb * net->sched_n_bands * 4;
-  if (int e = wowsr_ensure(ctx, net->trunk_ctr, ctr_bytes)) return e;
-  FusedParams T;
-  memset(&T, 0, sizeof T);
-  T.n_tasks = net->sched_n_tasks; T.n_win = nb; T.n_bands = net->sched_n_bands;
-  T.k_first = k_first; T.band_target = (unsigned int)net->sched_target;
-  T.rdb = rdb; T.n_rdb = n_rdb; T.h = h; T.w = w;
-  T.fp16 = body16; T.last_fp16 = tail16;
-  T.idesc_base = make_idesc_f16(128, 0, body16);
-  T.f32 = fl;
-  T.dense[0] = (uint16_t*)net->dense0.p; T.dense[1] = (uint16_t*)net->dense1.p;
-  T.lo = (uint16_t*)net->lo.p; T.rrdb = (float*)net->rrdb.p;
-  T.layers = (const TrunkLayerW*)net->trunk_tab.p;
-  T.tasks = (const SchedTask*)net->sched_tasks.p;
-  T.counters = (unsigned int*)net->trunk_ctr.p;
-  T.err_flag = (int*)net->err.p;
-  T.n_stage = (int)((SMEM_LIMIT - SMEM_SLACK - 2 * (size_t)TRUNK_WBUF_BYTES - 8192) / TC_ASTAGE32);
-  if (T.n_stage > TC_MAX_STAGES) T.n_stage = TC_MAX_STAGES;
-  if (wowsr_opt(ctx, "trunk_trace", 0) == rdb + 1) {  // per-task clock64 stamps of CTA 0 (wowsr_debug_trace reads them back)
-    if (int e = wowsr_ensure(ctx, ctx->trace_buf, 2 * 64 * 4 * 8)) return e;
-    WCUDA(ctx, cudaMemsetAsync(ctx->trace_buf.p, 0, 2 * 64 * 4 * 8, st));
-    T.trace = (long long*)ctx->trace_buf.p;
-  }
-  const size_t smem = (size_t)T.n_stage * TC_ASTAGE32 + 2 * (size_t)TRUNK_WBUF_BYTES + 8192 + SMEM_SLACK;
-  const int grid = std::min(ctx->sm_count, T.n_tasks);  // every CTA must be resident: tasks wait on each other
-  WCUDA(ctx, cudaMemsetAsync(net->trunk_ctr.p, 0, ctr_bytes, st));
-  rdb_fused_kernel<<<grid, TC_THREADS, smem, st>>>(tm[0][0], tm[0][1], tm[1][0], tm[1][1], T);
-  WLAUNCH_CHECK(ctx);
-  if (wowsr_opt(ctx, "trunk_debug", 0)) {  // bring-up aid: band counters after the launch (all must equal the target) + watchdog code
-    std::vector<unsigned int> c(ctr_bytes / 4);
-    int flag = 0;
-    cudaError_t ce = cudaStreamSynchronize(st);
-    cudaMemcpy(c.data(), net->trunk_ctr.p, ctr_bytes, cudaMemcpyDeviceToHost);
-    cudaMemcpy(&flag, net->err.p, 4, cudaMemcpyDeviceToHost);
-    size_t short_of = 0, first = c.size();
-    for (size_t i = 0; i < c.size(); i++)
-      if (c[i] != T.band_target) { if (!short_of++) first = i; }
-    fprintf(stderr, "[trunk_debug] rdb %d: sync=%s watchdog=%d grid=%d tasks=%d lag=%d bands=%d target=%u; %zu of %zu counters off target",
-            rdb, cudaGetErrorString(ce), flag, grid, T.n_tasks, net->sched_key[4], T.n_bands, T.band_target, short_of, c.size());
-    if (short_of) fprintf(stderr, " (first: slot %zu window %zu band %zu = %u)", first / ((size_t)nb * T.n_bands), first / T.n_bands % nb, first % T.n_bands, c[first]);
-    fprintf(stderr, "\n");
   }
   return 0;
 }
@@ -662,36 +510,8 @@ int rrdbnet_batch(wowsr_ctx* ctx, ConvNet* net, const uint8_t* img, long long pi
   void* cur = net->dense0.p;
   void* nxt = net->dense1.p;
   size_t li = 0;
-  const bool dataflow = hilo && wowsr_opt(ctx, "trunk_dataflow", 0) && wowsr_opt(ctx, "conv_impl", 0) == 0;
-  if (dataflow) {
-    if (int e = run_trunk_dataflow(ctx, net, nb, h, w, fl, body16, tail16, st)) return e;
-    li = (size_t)net->num_block * 15;
-    if ((net->num_block * 3) & 1) std::swap(cur, nxt);
-  }
-  // experimental fused tail (sched_kernel.cuh): convs trunk_fuse..5 of every RDB in one skewed persistent launch
-  const int fuse_k = (!dataflow && hilo && wowsr_opt(ctx, "conv_impl", 0) == 0 && h >= 8) ? (int)wowsr_opt(ctx, "trunk_fuse", 0) - 1 : -1;
-  CUtensorMap fuse_tm[2][2];
-  if (fuse_k >= 0) {
-    for (int b2 = 0; b2 < 2; b2++)
-      for (int v = 0; v < 2; v++)
-        if (int e = make_tmap(ctx, &fuse_tm[b2][v], b2 ? net->dense1.p : net->dense0.p, 192, w, h, nb, body16, v == 1, true)) return e;
-    WCUDA(ctx, cudaFuncSetAttribute(rdb_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
-  }
-  for (int b = 0; b < (dataflow ? 0 : net->num_block); b++)
+  for (int b = 0; b < net->num_block; b++)
     for (int r = 0; r < 3; r++) {
-      if (fuse_k >= 0) {
-        for (int k = 0; k < fuse_k; k++) {
-          LayerIO io;
-          io.in = cur; io.in_C = 192; io.Nw = nb; io.h = h; io.w = w;
-          io.act = 1;
-          io.out_t = cur; io.out_stride = 192; io.out_choff = 64 + 32 * k; io.out_fp16 = body16;
-          if (int e = run_conv(ctx, net, net->layers[li + k], io, st)) return e;
-        }
-        if (int e = run_rdb_fused(ctx, net, b * 3 + r, nb, h, w, fl, body16, tail16, fuse_tm, st)) return e;
-        li += 5;
-        std::swap(cur, nxt);
-        continue;
-      }
       for (int k = 0; k < 4; k++) {
         LayerIO io;
         io.in = cur; io.in_C = 192; io.Nw = nb; io.h = h; io.w = w;
@@ -726,8 +546,10 @@ int rrdbnet_batch(wowsr_ctx* ctx, ConvNet* net, const uint8_t* img, long long pi
       std::swap(cur, nxt);
     }
   WCUDA(ctx, cudaEventRecord(ctx->ev[2], st));
-  // experimental (ups_kernel.cuh): producers store at their own resolution, the upsample convs replicate through their tensor maps
-  const int fold = wowsr_opt(ctx, "tail_fold_upsample", 0) && wowsr_opt(ctx, "conv_impl", 0) == 0 ? 1 : 0;
+  // nearest-x2 folded into the consumer's TMA address generation (ups_kernel.cuh): producers store at their own resolution, the
+  // upsample convs replicate through zero-stride tensor maps.  Option tail_fold_upsample=0 (and the CUDA-core cross-check
+  // path) keeps the older producer-side 2x2 replicated store; both give bit-identical output (tests/test_gpu_rrdbnet.py).
+  const int fold = wowsr_opt(ctx, "tail_fold_upsample", 1) && wowsr_opt(ctx, "conv_impl", 0) == 0 ? 1 : 0;
   {  // conv_body + long skip, written nearest-x2 replicated for conv_up1
     LayerIO io;
     io.in = cur; io.in_C = 192; io.Nw = nb; io.h = h; io.w = w;
@@ -886,20 +708,6 @@ extern "C" int32_t wowsr_debug_trace(wowsr_ctx* ctx, int64_t* out, int32_t cap) 
   int n = cap < 512 ? cap : 512;
   if (cudaMemcpy(out, ctx->trace_buf.p, (size_t)n * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return WOWSR_ERR_CUDA;
   ctx->trace_counter = 0;
-  return n;
-}
-
-extern "C" int32_t wowsr_debug_fused_schedule(int32_t h, int32_t w, int32_t n_win, int32_t first_conv, int32_t lag, uint16_t* tasks,
-                                              int32_t cap, int32_t* info) {
-  SchedPlan P;
-  if (!(lag == -1 ? sched_build(P, h, w, n_win, first_conv - 1, 0, 48, 0) : sched_build(P, h, w, n_win, first_conv - 1, lag)))
-    return WOWSR_ERR_UNSUPPORTED;
-  if (info) {
-    info[0] = P.lag; info[1] = P.n_bands; info[2] = P.band_target_tiles; info[3] = P.strip_x0;
-    info[4] = P.band_rows; info[5] = P.n_layers; info[6] = TC_EPI_WARPS; info[7] = 0;
-  }
-  const int32_t n = (int32_t)P.tasks.size();
-  if (tasks && cap >= n) memcpy(tasks, P.tasks.data(), (size_t)n * sizeof(SchedTask));
   return n;
 }
 

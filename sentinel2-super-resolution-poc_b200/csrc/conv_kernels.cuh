@@ -498,8 +498,8 @@ __device__ __forceinline__ void epi_plain32(const EpiConst& E, float (&v)[32], c
 }
 
 // `fb` / `lb` = element index of channel ch0 of this lane's pixel in the warp-blocked fp32 / 16-bit buffers.
-// CG: read the residuals with ld.global.cg (L2 only) — needed when other SMs wrote them earlier in the SAME launch
-// (trunk_kernel.cuh); across launches the default path is fine because L1 is invalidated at launch boundaries.
+// CG: read the residuals with ld.global.cg (L2 only) — needed when other SMs wrote them earlier in the SAME launch;
+// across launches the default path is fine because L1 is invalidated at launch boundaries.
 template <bool CG = false>
 __device__ __forceinline__ void epi_res32(const EpiConst& E, float (&v)[32], const float* __restrict__ bias, long long fb, long long lb,
                                           bool valid, uint16_t* px, long long step, int u, int u_lim) {

@@ -1,5 +1,7 @@
-// EXPERIMENTAL — round-2 work in progress, NOT on the product path and NOT yet run on hardware (option tail_fold_upsample = 1;
-// opt-in pytest).  Whether the tensor map it needs can be encoded at all is the question tools/tma_stride0_probe.cu answers.
+// Product path of the two upsample convs (option tail_fold_upsample, default 1).  The zero-stride tensor map it needs is
+// accepted by the driver and replicates as required (tools/tma_stride0_probe.cu, profiles/r02_queue_tma_stride0_probe.txt);
+// output bit-identical to the producer-side replicated store, HR tail 7.5 -> 5.8 ms on 16 windows of 276x276
+// (profiles/r02_queue_fold_upsample.txt).
 //
 // conv3x3_tc_ups_kernel — conv_up1 / conv_up2 of RRDBNet.forward (cnn_super_resolution.py:150-153:
 // `lrelu(conv(F.interpolate(x, scale_factor=2, mode="nearest")))`) with the nearest-x2 upsample folded into the CONSUMER's

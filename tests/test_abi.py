@@ -120,7 +120,7 @@ def test_option_key_list_matches_the_keys_the_library_reads():
     block = src[src.index("kOptionKeys[] = {"):]
     listed = set(re.findall(r'"([a-z0-9_]+)"', block[:block.index("};")]))
     assert listed == read
-    for path in ("tests/test_gpu_rrdbnet.py", "tools/try_dataflow_perf.py", "tools/gpu_probe.py"):
+    for path in ("tests/test_gpu_rrdbnet.py", "tools/gpu_probe.py"):
         text = open(os.path.join(ROOT, path)).read()
         used = set(re.findall(r"\b((?:tc|trunk|conv|hist|mem)_[a-z0-9_]+)\s*=\s*\d", text)) | set(re.findall(r'"((?:tc|trunk|conv|hist|mem)_[a-z0-9_]+)"\s*:', text))
         assert used <= listed, (path, used - listed)

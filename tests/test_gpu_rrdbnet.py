@@ -256,64 +256,10 @@ def test_kernel_option_paths_agree(ws):
     assert np.abs(f - f_c).max() < tol and np.abs(f_c - ref_f).max() < 4 * tol
 
 
-@pytest.mark.skipif(os.environ.get("WOWSR_TEST_DATAFLOW") != "1",
-                    reason="experimental dataflow trunk (csrc/trunk_kernel.cuh): round-2 work in progress, opt-in")
-def test_experimental_dataflow_trunk_matches_layer_by_layer(ws):
-    """The persistent L2-resident trunk must reproduce the layer-by-layer path: same kernels' arithmetic per tile, so
-    float outputs agree to the operand-rounding noise floor and uint8 within 1 LSB."""
-    blocks = 2
-    sd = R.calibrate_conv_last(R.random_init_state_dict(4, blocks), blocks)
-    img = np.random.default_rng(13).integers(0, 256, (560, 290, 3), dtype=np.uint8)   # 3 x 2 windows of 276 wide: strips
-
-    def run(**opts):
-        h = ws.Handle(0)
-        for k, v in opts.items():
-            h.set_option(k, v)
-        h.load_rrdbnet(_tensors(sd, blocks), blocks, precision="bf16")
-        out = h.enhance_host(img, 256, want_float=True)
-        h.close()
-        return out
-
-    u8, f = run()
-    u8_d, f_d = run(trunk_dataflow=1)
-    ref_f = R.enhance_float(sd, img, blocks, 256)
-    tol = 0.005 * max(1.0, np.abs(ref_f).max())
-    assert np.abs(f - f_d).max() < tol and np.abs(f_d - ref_f).max() < 4 * tol
-    assert (np.abs(u8.astype(int) - u8_d.astype(int)) <= 1).mean() >= 0.999
-
-
-@pytest.mark.skipif(os.environ.get("WOWSR_TEST_FUSED") != "1",
-                    reason="experimental fused-tail launch (csrc/sched_kernel.cuh): round-2 work in progress, not yet run on hardware, opt-in")
-def test_experimental_fused_tail_matches_layer_by_layer(ws):
-    """convs f..5 of every RDB as one skewed persistent launch must reproduce the layer-by-layer path: the per-tile arithmetic
-    is the same, so float outputs agree to the operand-rounding noise floor and uint8 within 1 LSB."""
-    blocks = 2
-    sd = R.calibrate_conv_last(R.random_init_state_dict(4, blocks), blocks)
-    img = np.random.default_rng(13).integers(0, 256, (560, 290, 3), dtype=np.uint8)   # 3 x 2 windows of 276 wide: strips
-
-    def run(**opts):
-        h = ws.Handle(0)
-        for k, v in opts.items():
-            h.set_option(k, v)
-        h.load_rrdbnet(_tensors(sd, blocks), blocks, precision="bf16")
-        out = h.enhance_host(img, 256, want_float=True)
-        h.close()
-        return out
-
-    u8, f = run()
-    ref_f = R.enhance_float(sd, img, blocks, 256)
-    tol = 0.005 * max(1.0, np.abs(ref_f).max())
-    for opts in (dict(trunk_fuse=4), dict(trunk_fuse=4, trunk_lag=64), dict(trunk_fuse=3), dict(trunk_fuse=1)):
-        u8_d, f_d = run(**opts)
-        assert np.abs(f - f_d).max() < tol and np.abs(f_d - ref_f).max() < 4 * tol, opts
-        assert (np.abs(u8.astype(int) - u8_d.astype(int)) <= 1).mean() >= 0.999, opts
-
-
-@pytest.mark.skipif(os.environ.get("WOWSR_TEST_FOLD") != "1",
-                    reason="experimental folded upsample (csrc/ups_kernel.cuh): round-2 work in progress, not yet run on hardware, opt-in")
-def test_experimental_folded_upsample_is_bit_identical(ws):
-    """conv_up1 / conv_up2 reading the source-resolution buffer through a zero-stride tensor map see exactly the operands the
-    product path reads from its replicated buffers: outputs must be bit-identical."""
+def test_folded_upsample_is_bit_identical_to_replicated_store(ws):
+    """conv_up1 / conv_up2 reading the source-resolution buffer through a zero-stride tensor map (the default,
+    cnn_super_resolution.py:150-153 folded into the consumer's TMA address generation) see exactly the operands the older
+    producer-side replicated store gives them: outputs must be bit-identical (first hardware run: profiles/r02_queue_fold_upsample.txt)."""
     blocks = 1
     sd = R.calibrate_conv_last(R.random_init_state_dict(4, blocks), blocks)
     for shape, tile in (((150, 276), 256), ((300, 290), 128), ((40, 48), 256)):
