@@ -198,6 +198,14 @@ int32_t wowsr_get_timing(const wowsr_ctx* ctx, float* ms, int32_t cap);
  * launch selected with wowsr_set_option("tc_trace_layer", k) (k = 1-based launch index). Returns count. */
 int32_t wowsr_debug_trace(wowsr_ctx* ctx, int64_t* out, int32_t cap);
 
+/* Debug / test introspection of the rolling conv kernel's work list (csrc/roll_kernel.cuh; pure host function): the column
+ * segments that one launch over `n_win` windows of h x w assigns to `max_units` CTAs (pair = 0) or CTA pairs (pair = 1);
+ * columns x >= strip_x0 (strip_x0 = w: none) are covered by vertical tasks.  Each task is 8 int32:
+ * {window of rank 0, window of rank 1 (-1: dummy), run origin of rank 0, of rank 1, first output row, rows, 0, 0}; `off`
+ * receives units + 1 task offsets; info[4] = {units, horizontal units, offsets written, 0}.  Returns the task count. */
+int32_t wowsr_debug_roll_plan(int32_t n_win, int32_t h, int32_t w, int32_t strip_x0, int32_t pair, int32_t max_units,
+                              int32_t* tasks, int32_t cap_tasks, int32_t* off, int32_t cap_off, int32_t* info);
+
 /* ------------------------------------------------------------------------------------------ */
 /* EDSR-baseline x4 "farm SR" variant (super_resolution.py:92-124,196: cv2.dnn_superres          */
 /* DnnSuperResImpl.upsample with EDSR_x4.pb — third-party, parity unpinned)       */
@@ -207,6 +215,10 @@ int wowsr_load_edsr(wowsr_ctx* ctx, int32_t num_block, int32_t num_feat, float r
                     const float* const* tensors, int32_t n_tensors, int32_t precision);
 int wowsr_edsr_upsample_host(wowsr_ctx* ctx, const uint8_t* img_host, int32_t H, int32_t W,
                              uint8_t* out_host, float* out_f32_host);
+/* Same with device buffers (img [H,W,3] BGR u8 pitch W*3, out [4H,4W,3] pitch 4W*3, out_f32_dev may be NULL); returns after
+ * the stream has drained (the kernels' watchdog flag is read back).  wowsr_get_timing: 1 head, 2 resblocks, 3 upsampler + tail. */
+int wowsr_edsr_upsample_dev(wowsr_ctx* ctx, const uint8_t* img_dev, int32_t H, int32_t W, uint8_t* out_dev,
+                            float* out_f32_dev, void* stream);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

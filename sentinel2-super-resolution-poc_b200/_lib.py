@@ -70,8 +70,10 @@ _SIGS = {
                                      C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "wowsr_get_timing": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float), C.c_int32]),
     "wowsr_debug_trace": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
+    "wowsr_debug_roll_plan": (C.c_int32, [C.c_int32] * 6 + [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
     "wowsr_load_edsr": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.POINTER(C.c_void_p), C.c_int32, C.c_int32]),
     "wowsr_edsr_upsample_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "wowsr_edsr_upsample_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 
@@ -286,6 +288,12 @@ class Handle:
         return (out, outf) if want_float else out
 
 
+    @_locked
+    def edsr_upsample_dev(self, src_ptr, H, W, dst_ptr, dst_f32_ptr=None, stream=0):
+        self._check(self._L.wowsr_edsr_upsample_dev(self._h, C.c_void_p(src_ptr), H, W, C.c_void_p(dst_ptr),
+                                                    C.c_void_p(dst_f32_ptr) if dst_f32_ptr else None, C.c_void_p(stream)), "edsr_upsample_dev")
+
+
 # -- pure host helpers (no GPU needed) ----------------------------------------------------------
 
 def plan_windows(H, W, tile, pad=10):
@@ -310,6 +318,20 @@ def gaussian_taps(sigma):
     if n < 0:
         raise ValueError("sigma too large")
     return list(buf)[:n]
+
+
+def roll_plan(n_win, h, w, strip_x0=None, pair=True, max_units=74):
+    """Work list of the rolling conv kernel (csrc/roll_kernel.cuh) as ((n, 8) int32 tasks, offsets, info dict)."""
+    L = lib()
+    strip_x0 = w if strip_x0 is None else strip_x0
+    info = (C.c_int32 * 4)()
+    n = L.wowsr_debug_roll_plan(n_win, h, w, strip_x0, int(pair), max_units, None, 0, None, 0, info)
+    if n < 0:
+        raise ValueError("bad rolling-plan arguments")
+    tasks = np.empty((n, 8), dtype=np.int32)
+    off = np.empty(info[2], dtype=np.int32)
+    L.wowsr_debug_roll_plan(n_win, h, w, strip_x0, int(pair), max_units, tasks.ctypes.data, n, off.ctypes.data, len(off), info)
+    return tasks, off, {"units": info[0], "units_h": info[1]}
 
 
 _TABLES = {0: ("gam", np.uint16, 256), 1: ("cbrt", np.uint16, 3072), 2: ("lab_y", np.uint16, 256),

@@ -10,6 +10,7 @@
 #include "common.h"
 #include "conv_kernels.cuh"
 #include "ups_kernel.cuh"
+#include "roll_kernel.cuh"
 
 namespace {
 
@@ -25,6 +26,11 @@ struct LayerW {
   uint8_t* wpack32 = nullptr;  // same as [chunk of 32 ch][kx][j][co][32ch] (SWIZZLE_64B rows): streamed layers under option tc_chunk32
   uint8_t* wpack32_v = nullptr;
   size_t chunk_bytes32 = 0;
+  // rolling kernel, CTA pairs (roll_kernel.cuh): the stacked rows of every (chunk, tap) block split in halves,
+  // [rank][chunk][tap][3N/2 rows]; `pair_bytes` = one rank's image
+  uint8_t* wpair = nullptr;
+  uint8_t* wpair_v = nullptr;
+  size_t pair_bytes = 0;
   float* wsimple = nullptr;
   float* bias = nullptr;
 };
@@ -40,6 +46,9 @@ struct ConvNet {
   float* first_b = nullptr;
   std::vector<LayerW> layers;
   DevBuf dense0, dense1, feat, trunk, rrdb, lo, up1, hra, hrb, wins, winxy, err;
+  // rolling kernel: task lists per launch geometry (roll_plan_get)
+  struct RollPlanDev { int key[6]; DevBuf tasks, off; int units, units_h; };
+  std::vector<RollPlanDev> roll_plans;
 };
 
 void wowsr_net_free(ConvNet* n) {
@@ -49,11 +58,17 @@ void wowsr_net_free(ConvNet* n) {
     if (l.wpack_v) cudaFree(l.wpack_v);
     if (l.wpack32) cudaFree(l.wpack32);
     if (l.wpack32_v) cudaFree(l.wpack32_v);
+    if (l.wpair) cudaFree(l.wpair);
+    if (l.wpair_v) cudaFree(l.wpair_v);
     if (l.wsimple) cudaFree(l.wsimple);
     if (l.bias) cudaFree(l.bias);
   }
   if (n->first_w) cudaFree(n->first_w);
   if (n->first_b) cudaFree(n->first_b);
+  for (auto& rp : n->roll_plans) {
+    if (rp.tasks.p) cudaFree(rp.tasks.p);
+    if (rp.off.p) cudaFree(rp.off.p);
+  }
   DevBuf* bufs[] = {&n->dense0, &n->dense1, &n->feat, &n->trunk, &n->rrdb, &n->lo, &n->up1, &n->hra, &n->hrb, &n->wins, &n->winxy, &n->err};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
@@ -149,6 +164,26 @@ int upload_layer(wowsr_ctx* ctx, LayerW& L, const float* w, const float* b, int 
     WCUDA(ctx, cudaMalloc((void**)&L.wpack32_v, p32v.size()));
     WCUDA(ctx, cudaMemcpy(L.wpack32, p32.data(), p32.size(), cudaMemcpyHostToDevice));
     WCUDA(ctx, cudaMemcpy(L.wpack32_v, p32v.data(), p32v.size(), cudaMemcpyHostToDevice));
+  }
+  {  // CTA-pair images: rank r holds stacked rows [r * 3N/2, (r + 1) * 3N/2) of every (chunk, tap) block (3N/2 is a multiple of 8,
+     // so the swizzle phase of a row is the same in the split image)
+    const int rows_b = 3 * N / 2;
+    L.pair_bytes = L.chunk_bytes * L.n_chunks / 2;
+    std::vector<uint8_t> pp(2 * L.pair_bytes, 0), ppv(2 * L.pair_bytes, 0);
+    for (int r = 0; r < 2; r++)
+      for (int c = 0; c < L.n_chunks; c++) {
+        const size_t rb = (cin - c * 64 < 64) ? 64 : 128;  // operand row bytes of this chunk
+        for (int a = 0; a < 3; a++) {
+          const size_t src = (size_t)c * L.chunk_bytes + (size_t)a * (3 * N * rb) + (size_t)r * rows_b * rb;
+          const size_t dst = (size_t)r * L.pair_bytes + (size_t)c * (L.chunk_bytes / 2) + (size_t)a * (rows_b * rb);
+          memcpy(&pp[dst], &pack[src], rows_b * rb);
+          memcpy(&ppv[dst], &pack_v[src], rows_b * rb);
+        }
+      }
+    WCUDA(ctx, cudaMalloc((void**)&L.wpair, pp.size()));
+    WCUDA(ctx, cudaMalloc((void**)&L.wpair_v, ppv.size()));
+    WCUDA(ctx, cudaMemcpy(L.wpair, pp.data(), pp.size(), cudaMemcpyHostToDevice));
+    WCUDA(ctx, cudaMemcpy(L.wpair_v, ppv.data(), ppv.size(), cudaMemcpyHostToDevice));
   }
   std::vector<float> bias(64, 0.0f);
   for (int co = 0; co < cout; co++) bias[co] = b ? b[co] : 0.0f;
@@ -269,6 +304,217 @@ struct LayerIO {
   const WinDev* wins = nullptr;
 };
 
+// ---------------------------------------------------------------------------------------------
+// rolling kernel (roll_kernel.cuh): task lists and launch
+// ---------------------------------------------------------------------------------------------
+
+// Cuts the row sequence of all columns of a launch into `units` near-equal parts.  A column = one 128-pixel run over the
+// whole row axis of a window (horizontal: runs along x over the h rows of x < strip_x0; vertical: runs along y over the
+// strip's w - strip_x0 columns).  Pair launches put two columns side by side (the two CTAs of a pair), a dummy (-1) when
+// the count is odd.  Units [0, units_h) get the horizontal columns, the others the vertical ones, split in proportion to
+// the rows (+ 4 per column for the extra input rows and the junk pair).
+struct RollPlanHost {
+  std::vector<RollTask> tasks;
+  std::vector<int> off;
+  int units = 0, units_h = 0;
+};
+
+void roll_plan_build(RollPlanHost& R, int Nw, int h, int w, int strip_x0, bool pair, int max_units) {
+  struct Col { int n, u0; };
+  std::vector<Col> ch, cv;
+  const int runs_h = (strip_x0 + TC_RUN - 1) / TC_RUN, rem = w - strip_x0, runs_v = rem > 0 ? (h + TC_RUN - 1) / TC_RUN : 0;
+  for (int n = 0; n < Nw; n++) {
+    for (int r = 0; r < runs_h; r++) ch.push_back({n, r * TC_RUN});
+    for (int r = 0; r < runs_v; r++) cv.push_back({n, r * TC_RUN});
+  }
+  const int per = pair ? 2 : 1;
+  const long long pc_h = ((long long)ch.size() + per - 1) / per, pc_v = ((long long)cv.size() + per - 1) / per;  // (pair-)columns
+  const long long cost_h = pc_h * (h + 4), cost_v = pc_v * (rem + 4);
+  const int kMinRows = 8;  // do not cut segments shorter than this (each costs 2 extra input rows + a junk pair)
+  int units_v = 0;
+  if (pc_v > 0) {
+    units_v = (int)((double)max_units * cost_v / (double)(cost_h + cost_v) + 0.5);
+    if (units_v < 1) units_v = 1;
+    if (pc_h > 0 && units_v > max_units - 1) units_v = max_units - 1;
+    const long long cap = (pc_v * rem + kMinRows - 1) / kMinRows;
+    if (units_v > cap) units_v = (int)cap;
+  }
+  int units_h = 0;
+  if (pc_h > 0) {
+    units_h = max_units - units_v;
+    const long long cap = (pc_h * h + kMinRows - 1) / kMinRows;
+    if (units_h > cap) units_h = (int)cap;
+    if (units_h < 1) units_h = 1;
+  }
+  R.tasks.clear();
+  R.off.assign(1, 0);
+  auto cut = [&](const std::vector<Col>& cols, long long pcs, int len, int v_first, int units) {
+    if (units <= 0) return;
+    const long long total = pcs * len;
+    long long done = 0;
+    for (int k = 0; k < units; k++) {
+      const long long end = total * (k + 1) / units;  // exclusive end of this unit's share of the row sequence
+      while (done < end) {
+        const long long pcix = done / len;
+        const int r0 = (int)(done - pcix * len);
+        int take = (int)std::min<long long>(len - r0, end - done);
+        // never leave a sliver: a tail of fewer than kMinRows rows of this column goes to the same unit
+        if (len - (r0 + take) > 0 && len - (r0 + take) < kMinRows) take = len - r0;
+        if (take < kMinRows && r0 + take < len && k + 1 < units) { take = std::min(len - r0, kMinRows); }
+        RollTask T;
+        memset(&T, 0, sizeof T);
+        for (int q = 0; q < 2; q++) {
+          const size_t ci = (size_t)pcix * per + q;
+          if (q < per && ci < cols.size()) { T.n[q] = cols[ci].n; T.u0[q] = cols[ci].u0; }
+          else { T.n[q] = -1; T.u0[q] = 0; }
+        }
+        T.v0 = v_first + r0;
+        T.rows = take;
+        R.tasks.push_back(T);
+        done += take;
+      }
+      R.off.push_back((int)R.tasks.size());
+    }
+  };
+  cut(ch, pc_h, h, 0, units_h);
+  cut(cv, pc_v, rem, strip_x0, units_v);
+  R.units_h = units_h;
+  R.units = units_h + units_v;
+}
+
+int roll_plan_get(wowsr_ctx* ctx, ConvNet* net, int Nw, int h, int w, int strip_x0, bool pair, int max_units,
+                  const ConvNet::RollPlanDev** out, cudaStream_t st) {
+  const int key[6] = {Nw, h, w, strip_x0, pair ? 1 : 0, max_units};
+  for (const auto& rp : net->roll_plans)
+    if (memcmp(rp.key, key, sizeof key) == 0) { *out = &rp; return 0; }
+  RollPlanHost H;
+  roll_plan_build(H, Nw, h, w, strip_x0, pair, max_units);
+  if (H.units < 1 || H.tasks.empty()) return wowsr_fail(ctx, WOWSR_ERR_ARG, "rolling plan: nothing to do");
+  if (net->roll_plans.size() >= 16) {  // shapes change rarely (one per window size and layer resolution); keep the table small
+    for (auto& rp : net->roll_plans) { if (rp.tasks.p) cudaFree(rp.tasks.p); if (rp.off.p) cudaFree(rp.off.p); }
+    net->roll_plans.clear();
+  }
+  net->roll_plans.emplace_back();
+  ConvNet::RollPlanDev& D = net->roll_plans.back();
+  memcpy(D.key, key, sizeof key);
+  D.units = H.units; D.units_h = H.units_h;
+  if (int e = wowsr_ensure(ctx, D.tasks, H.tasks.size() * sizeof(RollTask))) return e;
+  if (int e = wowsr_ensure(ctx, D.off, H.off.size() * sizeof(int))) return e;
+  WCUDA(ctx, cudaMemcpyAsync(D.tasks.p, H.tasks.data(), H.tasks.size() * sizeof(RollTask), cudaMemcpyHostToDevice, st));
+  WCUDA(ctx, cudaMemcpyAsync(D.off.p, H.off.data(), H.off.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  WCUDA(ctx, cudaStreamSynchronize(st));  // H goes out of scope
+  *out = &D;
+  return 0;
+}
+
+template <int N, int MODE, bool PAIR>
+int roll_launch(wowsr_ctx* ctx, int grid, size_t smem, cudaStream_t st, const CUtensorMap& th, const CUtensorMap& tv, const CUtensorMap& th32,
+                const CUtensorMap& tv32, const ConvParams& P, const RollParams& Q) {
+  auto kern = conv3x3_roll_kernel<N, MODE, PAIR>;
+  static bool attr_set[8] = {false, false, false, false, false, false, false, false};  // per device
+  if (ctx->device < 8 ? !attr_set[ctx->device] : true) {
+    WCUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+    if (ctx->device < 8) attr_set[ctx->device] = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  WCUDA(ctx, cudaLaunchKernelEx(&cfg, kern, th, tv, th32, tv32, P, Q));
+  ctx->launches++;
+  return 0;
+}
+
+// Launches one conv layer through the rolling kernel.  Returns 1 when the layer is not eligible (the caller falls back to the
+// tile kernel): weights that do not fit next to two activation stages, the folded-upsample input, timing-only debug flags.
+int run_conv_roll(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, ConvParams& P, int mode, cudaStream_t st) {
+  const int N = L.N;
+  const int64_t roll = wowsr_opt(ctx, "roll", 1);
+  if (!roll || io.in_ups || (P.flags & (CF_DBG_NO_TMA | CF_DBG_NO_MMA | CF_DBG_NO_STORE))) return 1;
+  bool pair = wowsr_opt(ctx, "roll_pair", 1) != 0 && ctx->sm_count >= 2;
+  const size_t id_bytes = P.ident ? (pair ? 4096 : 8192) : 0;
+  // resident weights: full 64-channel chunks + the half-size remainder chunk
+  auto w_need = [&](bool pr) {
+    const size_t cb = pr ? L.chunk_bytes / 2 : L.chunk_bytes;
+    return cb * (size_t)(L.cin / 64) + (L.cin % 64 ? cb / 2 : 0);
+  };
+  auto stages_for = [&](bool pr) {
+    const size_t need = w_need(pr) + (P.ident ? (pr ? 4096 : 8192) : 0) + SMEM_SLACK;
+    return need >= SMEM_LIMIT ? 0 : (int)((SMEM_LIMIT - need) / TC_ASTAGE);
+  };
+  if (stages_for(pair) < 2) {
+    if (!pair && stages_for(true) >= 2 && ctx->sm_count >= 2 && wowsr_opt(ctx, "roll_pair", 1) != 0) pair = true;
+    else return 1;
+  }
+  (void)id_bytes;
+  int stages = stages_for(pair);
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  const int64_t optS = wowsr_opt(ctx, "tc_stages", 0);
+  if (optS >= 2 && optS < stages) stages = (int)optS;
+  P.n_stage = stages;
+  P.n_chunks = L.n_chunks;
+  P.chunk_ch = 64;
+  // geometry: the remainder strip (w % 128 columns) goes to vertical tasks under the same rule as the trunk layout
+  const int wm = io.w / TC_RUN * TC_RUN, rem = io.w - wm;
+  int max_units = pair ? ctx->sm_count / 2 : ctx->sm_count;
+  const int64_t optG = wowsr_opt(ctx, "roll_grid", 0);
+  if (optG > 0 && optG < max_units) max_units = (int)optG;
+  // a unit is horizontal or vertical for the whole launch (its weights are resident): the strip needs a unit of its own
+  const bool strip = rem > 0 && wm > 0 && io.h >= 64 && max_units >= 2 && !wowsr_opt(ctx, "tc_no_strip", 0);
+  const int strip_x0 = strip ? wm : io.w;
+  const ConvNet::RollPlanDev* plan = nullptr;
+  if (int e = roll_plan_get(ctx, net, io.Nw, io.h, io.w, strip_x0, pair, max_units, &plan, st)) return e;
+  CUtensorMap tmap, tmap_v, tmap32, tmap_v32;
+  const bool has_half = L.cin % 64 == 32;
+  if (int e = make_tmap(ctx, &tmap, io.in, io.in_C, io.w, io.h, io.Nw, L.fp16, false)) return e;
+  tmap_v = tmap; tmap32 = tmap;
+  if (has_half)
+    if (int e = make_tmap(ctx, &tmap32, io.in, io.in_C, io.w, io.h, io.Nw, L.fp16, false, true)) return e;
+  tmap_v32 = tmap32;
+  if (strip) {
+    if (int e = make_tmap(ctx, &tmap_v, io.in, io.in_C, io.w, io.h, io.Nw, L.fp16, true)) return e;
+    if (has_half)
+      if (int e = make_tmap(ctx, &tmap_v32, io.in, io.in_C, io.w, io.h, io.Nw, L.fp16, true, true)) return e;
+  }
+  RollParams Q;
+  memset(&Q, 0, sizeof Q);
+  Q.tasks = (const RollTask*)plan->tasks.p;
+  Q.task_off = (const int*)plan->off.p;
+  Q.units_h = plan->units_h;
+  Q.w_bytes = (int)w_need(pair);
+  Q.w_chunk_bytes = (int)(pair ? L.chunk_bytes / 2 : L.chunk_bytes);
+  if (pair) {
+    Q.wimg0 = L.wpair; Q.wimg1 = L.wpair + L.pair_bytes;
+    Q.wimg_v0 = L.wpair_v; Q.wimg_v1 = L.wpair_v + L.pair_bytes;
+  } else {
+    Q.wimg0 = Q.wimg1 = L.wpack;
+    Q.wimg_v0 = Q.wimg_v1 = L.wpack_v;
+  }
+  const size_t smem = (size_t)stages * TC_ASTAGE + Q.w_bytes + (P.ident ? (pair ? 4096 : 8192) : 0) + SMEM_SLACK;
+  const int grid = plan->units * (pair ? 2 : 1);
+#define ROLL_GO(NN, MM)                                                                                          \
+  return pair ? roll_launch<NN, MM, true>(ctx, grid, smem, st, tmap, tmap_v, tmap32, tmap_v32, P, Q)             \
+              : roll_launch<NN, MM, false>(ctx, grid, smem, st, tmap, tmap_v, tmap32, tmap_v32, P, Q)
+  if (N == 16) { ROLL_GO(16, EPI_GENERIC); }
+  if (N == 32) {
+    if (mode == EPI_PLAIN) { ROLL_GO(32, EPI_PLAIN); }
+    ROLL_GO(32, EPI_GENERIC);
+  }
+  if (mode == EPI_PLAIN) { ROLL_GO(64, EPI_PLAIN); }
+  if (mode == EPI_RES) { ROLL_GO(64, EPI_RES); }
+  ROLL_GO(64, EPI_GENERIC);
+#undef ROLL_GO
+}
+
 int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, cudaStream_t st) {
   ConvParams P;
   memset(&P, 0, sizeof P);
@@ -345,6 +591,16 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
 #undef SIMPLE
     WLAUNCH_CHECK(ctx);
     return 0;
+  }
+  {  // rolling kernel (roll_kernel.cuh) for every layer it can hold the weights of; the tile kernel below is the fallback
+    int mode_r = EPI_GENERIC;
+    if (!wowsr_opt(ctx, "tc_generic_epilogue", 0) && N >= 32 && !io.final && io.out_t && io.out_rep == 1 && !io.out_ps && !io.out_f32_b) {
+      if (!io.res1 && !io.res2 && !io.out_f32_a && !io.lo_in && !io.lo_out) mode_r = EPI_PLAIN;
+      else if (N == 64 && io.f32.wpb && (io.res1 != nullptr) != (io.lo_in != nullptr) && (io.out_f32_a || io.lo_out)) mode_r = EPI_RES;
+    }
+    ConvParams PR = P;
+    const int rr = run_conv_roll(ctx, net, L, io, PR, mode_r, st);
+    if (rr <= 0) return rr;
   }
   CUtensorMap tmap, tmap_v, tmap32, tmap_v32;
   if (io.in_ups) {
@@ -711,6 +967,18 @@ extern "C" int32_t wowsr_debug_trace(wowsr_ctx* ctx, int64_t* out, int32_t cap) 
   return n;
 }
 
+extern "C" int32_t wowsr_debug_roll_plan(int32_t n_win, int32_t h, int32_t w, int32_t strip_x0, int32_t pair, int32_t max_units,
+                                         int32_t* tasks, int32_t cap_tasks, int32_t* off, int32_t cap_off, int32_t* info) {
+  if (n_win < 1 || h < 1 || w < 1 || strip_x0 < 1 || strip_x0 > w || max_units < 1 || (strip_x0 < w && max_units < 2)) return WOWSR_ERR_ARG;
+  RollPlanHost H;
+  roll_plan_build(H, n_win, h, w, strip_x0, pair != 0, max_units);
+  if (info) { info[0] = H.units; info[1] = H.units_h; info[2] = (int32_t)H.off.size(); info[3] = 0; }
+  const int32_t n = (int32_t)H.tasks.size();
+  if (tasks && cap_tasks >= n) memcpy(tasks, H.tasks.data(), (size_t)n * sizeof(RollTask));
+  if (off && cap_off >= (int32_t)H.off.size()) memcpy(off, H.off.data(), H.off.size() * sizeof(int));
+  return n;
+}
+
 extern "C" int32_t wowsr_get_timing(const wowsr_ctx* ctx, float* ms, int32_t cap) {
   if (!ctx || !ms) return WOWSR_ERR_ARG;
   int n = cap < 4 ? cap : 4;
@@ -839,21 +1107,13 @@ extern "C" int wowsr_load_edsr(wowsr_ctx* ctx, int32_t num_block, int32_t num_fe
   return WOWSR_OK;
 }
 
-extern "C" int wowsr_edsr_upsample_host(wowsr_ctx* ctx, const uint8_t* img_host, int32_t H, int32_t W, uint8_t* out_host,
-                                        float* out_f32_host) {
-  if (!ctx || !img_host || !out_host || H < 1 || W < 1) return WOWSR_ERR_ARG;
-  ConvNet* net = ctx->edsr;
-  if (!net) return wowsr_fail(ctx, WOWSR_ERR_STATE, "wowsr_load_edsr has not been called");
-  DeviceGuard g(ctx->device);
-  cudaStream_t st = 0;
-  const size_t px = (size_t)H * W, in_bytes = px * 3, out_bytes = in_bytes * 16;
+// The EDSR forward on device buffers: img [H,W,3] BGR u8 (pitch W*3) -> out [4H,4W,3] u8 (pitch 4W*3), optional fp32 copy.
+static int edsr_forward(wowsr_ctx* ctx, ConvNet* net, const uint8_t* img_dev, int32_t H, int32_t W, uint8_t* out_dev, float* out_f32_dev,
+                        cudaStream_t st) {
+  const size_t px = (size_t)H * W;
   const bool f16 = net->body_fp16;
   const F32Layout fl = plain_blocked(1, H, W);
   const size_t pxb = (size_t)H * fl.wpb * 32 + (size_t)fl.rem * fl.hpb * 32;
-  if (int e = wowsr_ensure(ctx, ctx->img_in, in_bytes)) return e;
-  if (int e = wowsr_ensure(ctx, ctx->img_out, out_bytes)) return e;
-  if (out_f32_host)
-    if (int e = wowsr_ensure(ctx, ctx->img_out_f32, out_bytes * 4)) return e;
   if (int e = wowsr_ensure(ctx, net->dense0, px * 64 * 2)) return e;
   if (int e = wowsr_ensure(ctx, net->dense1, px * 64 * 2)) return e;
   if (int e = wowsr_ensure(ctx, net->feat, pxb * 64 * 4)) return e;
@@ -864,14 +1124,14 @@ extern "C" int wowsr_edsr_upsample_host(wowsr_ctx* ctx, const uint8_t* img_host,
   if (int e = wowsr_ensure(ctx, net->winxy, 8)) return e;
   WinDev wd{0, 0, 0, 0, 4 * W, 4 * H};
   int wxy[2] = {0, 0};
-  WCUDA(ctx, cudaMemcpyAsync(ctx->img_in.p, img_host, in_bytes, cudaMemcpyHostToDevice, st));
   WCUDA(ctx, cudaMemcpyAsync(net->wins.p, &wd, sizeof wd, cudaMemcpyHostToDevice, st));
   WCUDA(ctx, cudaMemcpyAsync(net->winxy.p, wxy, 8, cudaMemcpyHostToDevice, st));
   WCUDA(ctx, cudaStreamSynchronize(st));
+  WCUDA(ctx, cudaEventRecord(ctx->ev[0], st));
   {
     FirstParams F;
     memset(&F, 0, sizeof F);
-    F.img = (const uint8_t*)ctx->img_in.p; F.pitch = (long long)W * 3; F.cin = 3; F.win_xy = (const int*)net->winxy.p;
+    F.img = img_dev; F.pitch = (long long)W * 3; F.cin = 3; F.win_xy = (const int*)net->winxy.p;
     F.Nw = 1; F.h = H; F.w = W; F.weight = net->first_w; F.bias = net->first_b;
     F.f32 = fl;
     F.f32_a = (float*)net->feat.p; F.f32_b = (float*)net->trunk.p;
@@ -881,6 +1141,7 @@ extern "C" int wowsr_edsr_upsample_host(wowsr_ctx* ctx, const uint8_t* img_host,
     conv_first_kernel<<<grid, 128, 0, st>>>(F);
     WLAUNCH_CHECK(ctx);
   }
+  WCUDA(ctx, cudaEventRecord(ctx->ev[1], st));
   void* a = net->dense0.p;
   void* b = net->dense1.p;
   size_t li = 0;
@@ -902,6 +1163,7 @@ extern "C" int wowsr_edsr_upsample_host(wowsr_ctx* ctx, const uint8_t* img_host,
     io.out_t = b; io.out_stride = 64; io.out_fp16 = f16;
     if (int e = run_conv(ctx, net, net->layers[li++], io, st)) return e;
   }
+  WCUDA(ctx, cudaEventRecord(ctx->ev[2], st));
   for (int grp = 0; grp < 4; grp++) {  // up1: 64 -> 256, depth-to-space -> [2H,2W,64]
     LayerIO io;
     io.in = b; io.in_C = 64; io.Nw = 1; io.h = H; io.w = W;
@@ -919,12 +1181,45 @@ extern "C" int wowsr_edsr_upsample_host(wowsr_ctx* ctx, const uint8_t* img_host,
     io.in = net->hra.p; io.in_C = 64; io.Nw = 1; io.h = 4 * H; io.w = 4 * W;
     io.final = 1; io.final_scale = 1.0f; io.final_round = 1;
     for (int i = 0; i < 3; i++) io.final_add[i] = kEdsrMean[i];
-    io.out_u8 = (uint8_t*)ctx->img_out.p; io.out_u8_pitch = (long long)W * 4 * 3;
-    io.out_img_f32 = out_f32_host ? (float*)ctx->img_out_f32.p : nullptr; io.out_img_f32_pitch = (long long)W * 4 * 3;
+    io.out_u8 = out_dev; io.out_u8_pitch = (long long)W * 4 * 3;
+    io.out_img_f32 = out_f32_dev; io.out_img_f32_pitch = (long long)W * 4 * 3;
     io.wins = (const WinDev*)net->wins.p;
     if (int e = run_conv(ctx, net, net->layers[li++], io, st)) return e;
   }
-  if (int e = check_err_flag(ctx, net, st)) return e;
+  WCUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+  if (int e = check_err_flag(ctx, net, st)) return e;  // synchronises the stream
+  float t0 = 0, t1 = 0, t2 = 0;
+  cudaEventElapsedTime(&t0, ctx->ev[0], ctx->ev[1]);
+  cudaEventElapsedTime(&t1, ctx->ev[1], ctx->ev[2]);
+  cudaEventElapsedTime(&t2, ctx->ev[2], ctx->ev[3]);
+  ctx->timing[0] = t0 + t1 + t2; ctx->timing[1] = t0; ctx->timing[2] = t1; ctx->timing[3] = t2;
+  return WOWSR_OK;
+}
+
+extern "C" int wowsr_edsr_upsample_dev(wowsr_ctx* ctx, const uint8_t* img_dev, int32_t H, int32_t W, uint8_t* out_dev,
+                                       float* out_f32_dev, void* stream) {
+  if (!ctx || !img_dev || !out_dev || H < 1 || W < 1) return WOWSR_ERR_ARG;
+  if (!ctx->edsr) return wowsr_fail(ctx, WOWSR_ERR_STATE, "wowsr_load_edsr has not been called");
+  DeviceGuard g(ctx->device);
+  return edsr_forward(ctx, ctx->edsr, img_dev, H, W, out_dev, out_f32_dev, (cudaStream_t)stream);
+}
+
+extern "C" int wowsr_edsr_upsample_host(wowsr_ctx* ctx, const uint8_t* img_host, int32_t H, int32_t W, uint8_t* out_host,
+                                        float* out_f32_host) {
+  if (!ctx || !img_host || !out_host || H < 1 || W < 1) return WOWSR_ERR_ARG;
+  ConvNet* net = ctx->edsr;
+  if (!net) return wowsr_fail(ctx, WOWSR_ERR_STATE, "wowsr_load_edsr has not been called");
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = 0;
+  const size_t in_bytes = (size_t)H * W * 3, out_bytes = in_bytes * 16;
+  if (int e = wowsr_ensure(ctx, ctx->img_in, in_bytes)) return e;
+  if (int e = wowsr_ensure(ctx, ctx->img_out, out_bytes)) return e;
+  if (out_f32_host)
+    if (int e = wowsr_ensure(ctx, ctx->img_out_f32, out_bytes * 4)) return e;
+  WCUDA(ctx, cudaMemcpyAsync(ctx->img_in.p, img_host, in_bytes, cudaMemcpyHostToDevice, st));
+  if (int e = edsr_forward(ctx, net, (const uint8_t*)ctx->img_in.p, H, W, (uint8_t*)ctx->img_out.p,
+                           out_f32_host ? (float*)ctx->img_out_f32.p : nullptr, st))
+    return e;
   WCUDA(ctx, cudaMemcpyAsync(out_host, ctx->img_out.p, out_bytes, cudaMemcpyDeviceToHost, st));
   if (out_f32_host) WCUDA(ctx, cudaMemcpyAsync(out_f32_host, ctx->img_out_f32.p, out_bytes * 4, cudaMemcpyDeviceToHost, st));
   WCUDA(ctx, cudaStreamSynchronize(st));

@@ -1,5 +1,5 @@
 """CPU: the JSON line of ``bench.py --impl reference`` (the arm the driver runs beside ours) carries every key of the bench
-contract, and ranks other than 0 stay silent.  The CPU sample is shrunk to one block on 24 x 24 pixels so this runs in seconds;
+contract, and ranks other than 0 stay silent.  The CPU sample is shrunk to one block on 24 x 24 window pixels so this runs in seconds;
 the arithmetic timed is still the oracle port (oracle/rrdbnet_ref.py + oracle/wow_cv2.py)."""
 import argparse
 import json
@@ -12,10 +12,10 @@ import bench
 @pytest.fixture
 def fast_sample(monkeypatch):
     orig = bench.cpu_sample
-    monkeypatch.setattr(bench, "cpu_sample", lambda wl, blocks=23, sample_px=(266, 266): orig(wl, blocks=1, sample_px=(24, 24)))
+    monkeypatch.setattr(bench, "cpu_sample", lambda wl, **kw: orig(wl, blocks=1, n_windows=1, window_px=(24, 24), post_px=(64, 64)))
 
 
-@pytest.mark.parametrize("workload,gpus", [("cfg2", 1), ("scene", 8), ("post4096", 1)])
+@pytest.mark.parametrize("workload,gpus", [("cfg2", 1), ("scene", 8), ("post4096", 1), ("cfg3", 1)])
 def test_reference_arm_json_contract(fast_sample, capsys, monkeypatch, workload, gpus):
     monkeypatch.delenv("RANK", raising=False)
     args = argparse.Namespace(gpus=gpus, steps=2, warmup=1, workload=workload)
@@ -26,7 +26,7 @@ def test_reference_arm_json_contract(fast_sample, capsys, monkeypatch, workload,
     assert line["impl"] == "reference" and line["n_gpus"] == gpus and line["steps"] == 2 and line["warmup"] == 1
     assert line["metric"].startswith("output Mpix/s") and line["unit"] == "Mpix/s" and line["higher_is_better"] is True
     assert line["value"] > 0 and line["ms_per_step"] > 0 and line["vs_baseline"] is None and line["data"] == "synthetic"
-    assert line["dtype"] == "f32" and line["scaling"] in ("weak", "strong") and isinstance(line["config"]["workload"], str)
+    assert line["dtype"] == "f32" and line["scaling"] in ("weak", "strong", "replicas") and isinstance(line["config"]["workload"], str)
     cb = line["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["unit"] == "Mpix/s" and cb["value"] == line["value"] and cb["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
@@ -43,8 +43,19 @@ def test_workloads_name_the_baseline_configs():
     assert bench.workload("cfg2", 8)["H"] == 8 * 4096                       # weak scaling: 64 windows per GPU
     assert "1849 windows of 276x276" in bench.workload("scene", 8)["label"] and bench.workload("scene", 8)["H"] == 10980
     assert bench.FLOP_PER_LR_PX == 3456 + 69 * 479232 + 73728 + 294912 + 2 * 1179648 + 55296
+    assert bench.workload("scene", 1)["scaling"] == "strong" and bench.workload("cfg2", 2)["scaling"] == "weak"
+    assert bench.EDSR_FLOP_PER_LR_PX == 2 * 9 * (3 * 64 + 32 * 64 * 64 + 64 * 64 + 64 * 256) + 4 * (2 * 9 * 64 * 256) + 16 * (2 * 9 * 64 * 3)
     with pytest.raises(SystemExit):
         bench.workload("nope", 1)
+
+
+def test_default_workload_is_the_north_star_scene(monkeypatch):
+    import sys
+    seen = {}
+    monkeypatch.setattr(bench, "run_ours", lambda a: seen.update(vars(a)))
+    monkeypatch.setattr(sys, "argv", ["bench.py"])
+    bench.main()
+    assert seen["workload"] == "scene" and seen["gpus"] == 1 and seen["warmup"] >= 3
 
 
 def test_clock_sampler_parses_nvidia_smi_lines():

@@ -16,7 +16,7 @@ for r in csv.DictReader(lines):
 ks = list(byid.values())
 i0 = [i for i, k in enumerate(ks) if "conv_first" in k["name"]][0]
 step = ks[i0:i0 + 354]
-tc = [k for k in step if "conv3x3_tc" in k["name"]]
+tc = [k for k in step if "conv3x3_tc" in k["name"] or "conv3x3_roll" in k["name"]]
 T, RD, WR = "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum"
 has_dram = RD in tc[0]
 px = windows * side * side
@@ -38,12 +38,12 @@ fls = [73728, 294912, 1179648, 1179648, 55296]
 for nm, k, f in zip(["conv_body", "conv_up1", "conv_up2", "conv_hr", "conv_last"], tc[345:], fls):
     extra = f"  dram {k[RD]/px:7.1f} read {k[WR]/px:7.1f} written B/LR-px" if has_dram else ""
     print(f"{nm}: {k[T]/1e3:8.1f} us  {px*f/k[T]/1e3:5.0f} TFLOP/s algorithmic  {100*k[T]/tot:4.1f}% of conv time{extra}")
-print(f"all {len(tc)} conv3x3_tc_kernel launches: {tot/1e6:.2f} ms -> {px*35853696/tot/1e3:.0f} TFLOP/s algorithmic")
+print(f"all {len(tc)} tensor-core conv launches: {tot/1e6:.2f} ms -> {px*35853696/tot/1e3:.0f} TFLOP/s algorithmic")
 if has_dram:
     b = sum(k[RD] + k[WR] for k in tc)
     print(f"DRAM traffic of those launches: {b/1e9:.1f} GB ({b/tot/1e3:.2f} TB/s while running, {px*35853696/b:.0f} FLOP/B)")
     if len(sys.argv) > 4:
-        json.dump({"tc_launches": len(tc), "time_ms": tot / 1e6, "dram_bytes": b, "windows": windows}, open(sys.argv[4], "w"))
+        json.dump({"tc_launches": len(tc), "time_ms": tot / 1e6, "dram_bytes": b, "windows": windows, "side": side}, open(sys.argv[4], "w"))
 for k in step:
     if "conv" not in k["name"]:
         print(f"{k['name'][:70]} grid {k['grid']}: {k[T]/1e3:.1f} us")
