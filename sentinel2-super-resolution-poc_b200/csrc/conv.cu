@@ -361,6 +361,8 @@ void roll_plan_build(RollPlanHost& R, int Nw, int h, int w, int strip_x0, bool p
         // never leave a sliver: a tail of fewer than kMinRows rows of this column goes to the same unit
         if (len - (r0 + take) > 0 && len - (r0 + take) < kMinRows) take = len - r0;
         if (take < kMinRows && r0 + take < len && k + 1 < units) { take = std::min(len - r0, kMinRows); }
+        // segments start on even rows: row v of a column lives in ring slot v % RING and a ring pair holds rows (2j, 2j + 1)
+        if (r0 + take < len && (take & 1)) take++;
         RollTask T;
         memset(&T, 0, sizeof T);
         for (int q = 0; q < 2; q++) {
@@ -407,10 +409,10 @@ int roll_plan_get(wowsr_ctx* ctx, ConvNet* net, int Nw, int h, int w, int strip_
   return 0;
 }
 
-template <int N, int MODE, bool PAIR>
+template <int N, int MODE, bool PAIR, bool UPS = false>
 int roll_launch(wowsr_ctx* ctx, int grid, size_t smem, cudaStream_t st, const CUtensorMap& th, const CUtensorMap& tv, const CUtensorMap& th32,
                 const CUtensorMap& tv32, const ConvParams& P, const RollParams& Q) {
-  auto kern = conv3x3_roll_kernel<N, MODE, PAIR>;
+  auto kern = conv3x3_roll_kernel<N, MODE, PAIR, UPS>;
   static bool attr_set[8] = {false, false, false, false, false, false, false, false};  // per device
   if (ctx->device < 8 ? !attr_set[ctx->device] : true) {
     WCUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
@@ -439,7 +441,10 @@ int roll_launch(wowsr_ctx* ctx, int grid, size_t smem, cudaStream_t st, const CU
 int run_conv_roll(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, ConvParams& P, int mode, cudaStream_t st) {
   const int N = L.N;
   const int64_t roll = wowsr_opt(ctx, "roll", 1);
-  if (!roll || io.in_ups || (P.flags & (CF_DBG_NO_TMA | CF_DBG_NO_MMA | CF_DBG_NO_STORE))) return 1;
+  if (!roll || (P.flags & (CF_DBG_NO_TMA | CF_DBG_NO_MMA | CF_DBG_NO_STORE))) return 1;
+  if (io.in_ups && (L.cin != 64 || N != 64 || mode != EPI_PLAIN || (io.w & 1) || (io.h & 1) || io.in_C != 64))
+    return wowsr_fail(ctx, WOWSR_ERR_UNSUPPORTED, "folded upsample: 64 -> 64 layers with the plain epilogue at an even resolution only");
+  const size_t astage = io.in_ups ? 2 * (size_t)TC_UPS_ROWB : (size_t)TC_ASTAGE;
   bool pair = wowsr_opt(ctx, "roll_pair", 1) != 0 && ctx->sm_count >= 2;
   const size_t id_bytes = P.ident ? (pair ? 4096 : 8192) : 0;
   // resident weights: full 64-channel chunks + the half-size remainder chunk
@@ -449,7 +454,7 @@ int run_conv_roll(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& 
   };
   auto stages_for = [&](bool pr) {
     const size_t need = w_need(pr) + (P.ident ? (pr ? 4096 : 8192) : 0) + SMEM_SLACK;
-    return need >= SMEM_LIMIT ? 0 : (int)((SMEM_LIMIT - need) / TC_ASTAGE);
+    return need >= SMEM_LIMIT ? 0 : (int)((SMEM_LIMIT - need) / astage);
   };
   if (stages_for(pair) < 2) {
     if (!pair && stages_for(true) >= 2 && ctx->sm_count >= 2 && wowsr_opt(ctx, "roll_pair", 1) != 0) pair = true;
@@ -475,13 +480,17 @@ int run_conv_roll(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& 
   if (int e = roll_plan_get(ctx, net, io.Nw, io.h, io.w, strip_x0, pair, max_units, &plan, st)) return e;
   CUtensorMap tmap, tmap_v, tmap32, tmap_v32;
   const bool has_half = L.cin % 64 == 32;
-  if (int e = make_tmap(ctx, &tmap, io.in, io.in_C, io.w, io.h, io.Nw, L.fp16, false)) return e;
+  if (io.in_ups) {
+    if (int e = make_tmap_ups(ctx, &tmap, io.in, 64, io.w / 2, io.h / 2, io.Nw, L.fp16, false)) return e;
+  } else if (int e = make_tmap(ctx, &tmap, io.in, io.in_C, io.w, io.h, io.Nw, L.fp16, false)) return e;
   tmap_v = tmap; tmap32 = tmap;
   if (has_half)
     if (int e = make_tmap(ctx, &tmap32, io.in, io.in_C, io.w, io.h, io.Nw, L.fp16, false, true)) return e;
   tmap_v32 = tmap32;
   if (strip) {
-    if (int e = make_tmap(ctx, &tmap_v, io.in, io.in_C, io.w, io.h, io.Nw, L.fp16, true)) return e;
+    if (io.in_ups) {
+      if (int e = make_tmap_ups(ctx, &tmap_v, io.in, 64, io.w / 2, io.h / 2, io.Nw, L.fp16, true)) return e;
+    } else if (int e = make_tmap(ctx, &tmap_v, io.in, io.in_C, io.w, io.h, io.Nw, L.fp16, true)) return e;
     if (has_half)
       if (int e = make_tmap(ctx, &tmap_v32, io.in, io.in_C, io.w, io.h, io.Nw, L.fp16, true, true)) return e;
   }
@@ -499,8 +508,11 @@ int run_conv_roll(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& 
     Q.wimg0 = Q.wimg1 = L.wpack;
     Q.wimg_v0 = Q.wimg_v1 = L.wpack_v;
   }
-  const size_t smem = (size_t)stages * TC_ASTAGE + Q.w_bytes + (P.ident ? (pair ? 4096 : 8192) : 0) + SMEM_SLACK;
+  const size_t smem = (size_t)stages * astage + Q.w_bytes + (P.ident ? (pair ? 4096 : 8192) : 0) + SMEM_SLACK;
   const int grid = plan->units * (pair ? 2 : 1);
+  if (io.in_ups)
+    return pair ? roll_launch<64, EPI_PLAIN, true, true>(ctx, grid, smem, st, tmap, tmap_v, tmap32, tmap_v32, P, Q)
+                : roll_launch<64, EPI_PLAIN, false, true>(ctx, grid, smem, st, tmap, tmap_v, tmap32, tmap_v32, P, Q);
 #define ROLL_GO(NN, MM)                                                                                          \
   return pair ? roll_launch<NN, MM, true>(ctx, grid, smem, st, tmap, tmap_v, tmap32, tmap_v32, P, Q)             \
               : roll_launch<NN, MM, false>(ctx, grid, smem, st, tmap, tmap_v, tmap32, tmap_v32, P, Q)

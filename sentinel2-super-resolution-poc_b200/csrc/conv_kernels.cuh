@@ -497,31 +497,44 @@ __device__ __forceinline__ void epi_plain32(const EpiConst& E, float (&v)[32], c
   epi_store16_quad(v, E.out_fp16, px, step, u, u_lim);
 }
 
-// `fb` / `lb` = element index of channel ch0 of this lane's pixel in the warp-blocked fp32 / 16-bit buffers.
-// CG: read the residuals with ld.global.cg (L2 only) — needed when other SMs wrote them earlier in the SAME launch;
-// across launches the default path is fine because L1 is invalidated at launch boundaries.
+// Residual 1 of epi_res32 as raw 16-byte pieces, so a caller can issue the loads EARLY (the rolling kernel fetches them before
+// it waits for the accumulators: their DRAM latency was most of a rdb.conv5 epilogue iteration).  lo path: 4 pieces (32 bf16),
+// fp32 path: 8 pieces (32 floats).
 template <bool CG = false>
-__device__ __forceinline__ void epi_res32(const EpiConst& E, float (&v)[32], const float* __restrict__ bias, long long fb, long long lb,
-                                          bool valid, uint16_t* px, long long step, int u, int u_lim) {
-  float t[32];
-  if (E.lo_in) {  // hi part already in the accumulator (identity K-step); 4 x 16 bytes of bf16 lo
+__device__ __forceinline__ void epi_res_fetch(const EpiConst& E, long long fb, long long lb, bool valid, uint4 (&w)[8]) {
+  if (E.lo_in) {
     const uint4* r = reinterpret_cast<const uint4*>(E.lo_in + lb);
 #pragma unroll
+    for (int i = 0; i < 4; i++) w[i] = valid ? (CG ? __ldcg(r + i * 32) : r[i * 32]) : make_uint4(0u, 0u, 0u, 0u);
+  } else {
+    const uint4* r = reinterpret_cast<const uint4*>(E.res1 + fb);
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = valid ? (CG ? __ldcg(r + i * 32) : r[i * 32]) : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+__device__ __forceinline__ void epi_res_unpack(const EpiConst& E, const uint4* w, float (&t)[32]) {
+  if (E.lo_in) {  // hi part already in the accumulator (identity K-step); 4 x 16 bytes of bf16 lo
+#pragma unroll
     for (int i = 0; i < 4; i++) {
-      const uint4 w = valid ? (CG ? __ldcg(r + i * 32) : r[i * 32]) : make_uint4(0u, 0u, 0u, 0u);
-      t[8 * i + 0] = __uint_as_float(w.x << 16); t[8 * i + 1] = __uint_as_float(w.x & 0xFFFF0000u);
-      t[8 * i + 2] = __uint_as_float(w.y << 16); t[8 * i + 3] = __uint_as_float(w.y & 0xFFFF0000u);
-      t[8 * i + 4] = __uint_as_float(w.z << 16); t[8 * i + 5] = __uint_as_float(w.z & 0xFFFF0000u);
-      t[8 * i + 6] = __uint_as_float(w.w << 16); t[8 * i + 7] = __uint_as_float(w.w & 0xFFFF0000u);
+      t[8 * i + 0] = __uint_as_float(w[i].x << 16); t[8 * i + 1] = __uint_as_float(w[i].x & 0xFFFF0000u);
+      t[8 * i + 2] = __uint_as_float(w[i].y << 16); t[8 * i + 3] = __uint_as_float(w[i].y & 0xFFFF0000u);
+      t[8 * i + 4] = __uint_as_float(w[i].z << 16); t[8 * i + 5] = __uint_as_float(w[i].z & 0xFFFF0000u);
+      t[8 * i + 6] = __uint_as_float(w[i].w << 16); t[8 * i + 7] = __uint_as_float(w[i].w & 0xFFFF0000u);
     }
   } else {
-    const float4* r = reinterpret_cast<const float4*>(E.res1 + fb);
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-      const float4 w = valid ? (CG ? __ldcg(r + i * 32) : r[i * 32]) : make_float4(0.f, 0.f, 0.f, 0.f);
-      t[4 * i] = w.x; t[4 * i + 1] = w.y; t[4 * i + 2] = w.z; t[4 * i + 3] = w.w;
+      t[4 * i] = __uint_as_float(w[i].x); t[4 * i + 1] = __uint_as_float(w[i].y);
+      t[4 * i + 2] = __uint_as_float(w[i].z); t[4 * i + 3] = __uint_as_float(w[i].w);
     }
   }
+}
+
+// `fb` / `lb` = element index of channel ch0 of this lane's pixel in the warp-blocked fp32 / 16-bit buffers.
+// `t` = residual 1 (epi_res_fetch + epi_res_unpack).
+template <bool CG = false>
+__device__ __forceinline__ void epi_res32_t(const EpiConst& E, float (&v)[32], float (&t)[32], const float* __restrict__ bias, long long fb,
+                                            long long lb, bool valid, uint16_t* px, long long step, int u, int u_lim) {
   epi_bias32(v, bias);
 #pragma unroll
   for (int i = 0; i < 32; i++) v[i] = __fadd_rn(__fmul_rn(v[i], E.scale1), t[i]);
@@ -568,6 +581,18 @@ __device__ __forceinline__ void epi_res32(const EpiConst& E, float (&v)[32], con
     }
   }
   epi_store_quad(pk, px, step, u, u_lim);
+}
+
+// CG: read the residuals with ld.global.cg (L2 only) — needed when other SMs wrote them earlier in the SAME launch;
+// across launches the default path is fine because L1 is invalidated at launch boundaries.
+template <bool CG = false>
+__device__ __forceinline__ void epi_res32(const EpiConst& E, float (&v)[32], const float* __restrict__ bias, long long fb, long long lb,
+                                          bool valid, uint16_t* px, long long step, int u, int u_lim) {
+  uint4 w[8];
+  epi_res_fetch<CG>(E, fb, lb, valid, w);
+  float t[32];
+  epi_res_unpack(E, w, t);
+  epi_res32_t<CG>(E, v, t, bias, fb, lb, valid, px, step, u, u_lim);
 }
 
 // ---------------------------------------------------------------------------------------------

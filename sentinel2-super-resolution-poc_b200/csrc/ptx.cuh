@@ -192,9 +192,15 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
-// arrive on a barrier that may live in the peer CTA (`bar` is a shared::cluster address)
+// Arrive on a barrier that may live in the peer CTA (`bar` is a shared::cluster address).  RELAXED: the callers hand back TMEM
+// accumulator slots, which tcgen05.fence::before_thread_sync / ::after_thread_sync order; no generic-proxy data travels with the
+// signal.  (.release.cluster compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR, which waits for every outstanding global store
+// of the warp: measured 50 % of all stall samples of an epilogue-heavy layer, profiles/r02_ncu_roll_first.txt.)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 // TMA tile load whose completion bytes are counted on a barrier of EITHER CTA of the pair (`bar`: shared::cluster address)
 __device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {

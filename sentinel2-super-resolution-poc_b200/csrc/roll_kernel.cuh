@@ -9,15 +9,19 @@
 //     (the tile kernel reads R + 2 input rows for R output rows, 1.25x for R = 8) and no tile-edge MMAs with fewer stacked
 //     taps exist.  Every tcgen05.mma of a launch has the same shape (N_eff = 3 * Cout, accumulate), so the whole weight set
 //     can be split in halves between the two CTAs of a pair (below) with ONE image per CTA.
-//   * Ring layout: SLOTS = 512 / Cout column blocks; RING = SLOTS - 2 of them hold output rows (row r lives in slot r % RING),
-//     the last two MIRROR slots 0 and 1: the MMA of a centre row in slot RING-1 (RING-2) writes its third (second and third)
-//     block into the mirror instead of wrapping around, and the epilogue adds real + mirror for rows in slots 0 and 1.
+//   * Ring layout: SLOTS = 512 / Cout column blocks; RING = SLOTS - 2 of them hold output rows, the last two MIRROR slots 0
+//     and 1: the MMA of a centre row in slot RING-1 (RING-2) writes its third (second and third) block into the mirror instead
+//     of wrapping around, and the epilogue adds real + mirror for rows in slots 0 and 1.  Output row v of a column ALWAYS lives
+//     in slot v % RING (v = row index inside the window), so the order in which a pixel's partial sums are added depends on the
+//     window geometry only — not on the batch, the cut points of the work list or the grid: a window gives bit-identical
+//     results alone, inside any batch and on any number of GPUs (tests/test_gpu_full_size.py, tools/multigpu_check.py).
 //   * The epilogue drains output rows in pairs as soon as the input row below them has been multiplied, and CLEARS the slots
 //     (tcgen05.st) before handing them back, so the issuer never needs an overwrite-instead-of-accumulate MMA.
 //   * Work is a host-built list of column segments (RollTask): the row sequence of all columns is cut into equal parts, one
 //     per CTA (or pair), so the launch is balanced to a few rows whatever the window count; a segment costs two extra input
-//     rows.  Segments follow each other in the ring separated by one junk pair (it absorbs the taps that fall outside the
-//     segment), which keeps the issue loop free of special cases.
+//     rows and two junk pairs (they absorb the taps that fall outside the segment and are cleared like any other pair), which
+//     keeps the issue loop free of special cases.  Pair slots are handed back and forth with per-slot parity bits because a
+//     new segment starts wherever its first row index puts it in the ring.
 //   * PAIR = true: clusters of two CTAs (tcgen05 cta_group::2, M = 256).  Each CTA loads its own 128-pixel runs and drains its
 //     own TMEM; the leader issues every MMA; the stacked weight rows are split in halves between the two CTAs' shared memory,
 //     so each SM fetches only half of B per MMA (measured 49.3 instead of 56 cycles at N_eff = 96, profiles/r02_queue_mma_2cta_bench.txt)
@@ -110,12 +114,13 @@ __device__ __forceinline__ void roll_mma_group(uint32_t col, uint64_t a, uint64_
 // Run-axis taps [KX0, KX1) of both input rows of one stage (one 64-channel chunk, or the 32-channel remainder chunk when HALF).
 // ROWS_B = stacked weight rows per (chunk, tap) block in THIS CTA's image.  Descriptor units are 16 bytes: an operand row is
 // 128 B (64 B when HALF), the second row of a stage starts 130 operand rows after the first, a tap shifts A by one operand row.
-template <int N, bool PAIR, bool HALF, int KX0, int KX1>
+template <int N, bool PAIR, bool HALF, int KX0, int KX1, bool UPS = false>
 __device__ __forceinline__ void roll_issue_taps(bool leader, uint32_t col0, uint32_t col1, uint64_t ad, uint64_t bd, uint32_t idesc) {
   constexpr int ROWS_B = PAIR ? 3 * N / 2 : 3 * N;
   constexpr int RU = HALF ? 4 : 8;            // operand row in descriptor units
   constexpr int NKS = HALF ? 2 : 4;
-  constexpr int ROW1 = TC_AROWS * RU;          // second input row of the stage
+  // second input row of the stage: 130 operand rows after the first; folded upsample: its own 1024-aligned 132-pixel box
+  constexpr int ROW1 = UPS ? TC_UPS_ROWB / 16 : TC_AROWS * RU;
   if (leader) {
 #pragma unroll
     for (int kx = KX0; kx < KX1; kx++) {
@@ -126,7 +131,10 @@ __device__ __forceinline__ void roll_issue_taps(bool leader, uint32_t col0, uint
   }
 }
 
-template <int N, int MODE, bool PAIR>
+// UPS: the input is at HALF the layer resolution and the nearest-x2 upsample (cnn_super_resolution.py:150-153) is folded into
+// the TMA address generation exactly like conv3x3_tc_ups_kernel (ups_kernel.cuh): a zero-stride 5-D tensor map replicates
+// along the run axis (one 132-pixel box per stage row, A descriptors start one pixel in), the producer halves the row index.
+template <int N, int MODE, bool PAIR, bool UPS = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__ CUtensorMap tmap_v,
                     const __grid_constant__ CUtensorMap tmap_h32, const __grid_constant__ CUtensorMap tmap_v32, const ConvParams P,
@@ -135,6 +143,8 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_con
   constexpr int RING = SLOTS - 2;          // slots that hold output rows; the last two mirror slots 0 and 1
   constexpr int NP = RING / 2;             // row pairs in the ring
   constexpr uint32_t TMEM_COLS = SLOTS * N;
+  constexpr int ASTAGE = UPS ? 2 * TC_UPS_ROWB : TC_ASTAGE;  // bytes of one stage slot (two input rows)
+  static_assert(!UPS || (N == 64 && MODE == EPI_PLAIN), "folded upsample: the two 64 -> 64 upsample convs only");
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;
@@ -146,7 +156,7 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_con
   const int t0 = Q.task_off[unit], t1 = Q.task_off[unit + 1];
   const uint32_t smem_base = (ptx::smem_u32(smem) + 1023u) & ~1023u;
   const uint32_t a_smem = smem_base;
-  const uint32_t w_smem = a_smem + P.n_stage * TC_ASTAGE;
+  const uint32_t w_smem = a_smem + P.n_stage * ASTAGE;
   const uint32_t id_smem = w_smem + Q.w_bytes;  // identity operand of the split trunk (P.ident): 64 (pair: 32) rows x 128 B
   const uint32_t id_bytes = P.ident ? (PAIR ? 4096u : 8192u) : 0u;
   const uint32_t ctl_addr = id_smem + id_bytes;
@@ -218,6 +228,9 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_con
     const bool leader = ptx::elect_one();
     int stage = 0;
     uint32_t aphase = 0;
+    const bool tr = P.trace != nullptr && blockIdx.x == 0;  // debug: cycle attribution of CTA 0 (tools/roll_trace.py)
+    long long tr_wait = 0, tr_n = 0;
+    const long long tr_t0 = tr ? clock64() : 0;
     for (int t = t0; t < t1; t++) {
       const RollTaskView T = roll_task(Q.tasks, t, rank);
       const int n = T.n < 0 ? P.Nw : T.n;  // a dummy partner reads out of bounds: zero fill
@@ -225,24 +238,37 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_con
       const int ns = (T.rows + 3) >> 1;
       for (int s = 0; s < ns; s++) {
         for (int c = 0; c < P.n_chunks; c++) {
+          const long long tw0 = tr ? clock64() : 0;
           if (!ptx::mbar_wait_wd(ptx::smem_u32(&ctl->a_empty[stage]), aphase ^ 1, wd)) tc_fail(P, 12);
+          if (tr) { tr_wait += clock64() - tw0; tr_n++; }
           if (leader) {
             const bool half_c = (P.cin - c * 64) < 64;
             const uint32_t bytes = half_c ? TC_ABYTES : 2 * TC_ABYTES;
             const uint32_t full = ptx::smem_u32(&ctl->a_full[stage]);
-            if constexpr (PAIR) {
+            if constexpr (UPS) {
+              const uint32_t bar = PAIR ? ptx::mapa(full, 0) : full;
+              if (!PAIR || rank == 0) ptx::mbar_arrive_expect_tx(full, (PAIR ? 2u : 1u) * 2u * TC_UPS_BOXB);
+#pragma unroll
+              for (int half = 0; half < 2; half++) {
+                const int row_up = T.v0 - 1 + 2 * s + half;  // row of the upsampled image; (-1) >> 1 = -1 and (2h) >> 1 = h are out of bounds: zero fill
+                const uint32_t dst = a_smem + stage * ASTAGE + half * TC_UPS_ROWB;
+                if constexpr (PAIR) ptx::tma_load_5d_pair(dst, &tmap, bar, 0, 0, (u0 >> 1) - 1, row_up >> 1, n);
+                else ptx::tma_load_5d(dst, &tmap, bar, 0, 0, (u0 >> 1) - 1, row_up >> 1, n);
+              }
+            } else if constexpr (PAIR) {
               if (rank == 0) ptx::mbar_arrive_expect_tx(full, 2 * bytes);  // both CTAs' boxes complete on the leader's barrier
-              ptx::tma_load_4d_pair(a_smem + stage * TC_ASTAGE, half_c ? &tmap32 : &tmap, ptx::mapa(full, 0), c * 64, u0 - 1,
+              ptx::tma_load_4d_pair(a_smem + stage * ASTAGE, half_c ? &tmap32 : &tmap, ptx::mapa(full, 0), c * 64, u0 - 1,
                                     T.v0 - 1 + 2 * s, n);
             } else {
               ptx::mbar_arrive_expect_tx(full, bytes);
-              ptx::tma_load_4d(a_smem + stage * TC_ASTAGE, half_c ? &tmap32 : &tmap, full, c * 64, u0 - 1, T.v0 - 1 + 2 * s, n);
+              ptx::tma_load_4d(a_smem + stage * ASTAGE, half_c ? &tmap32 : &tmap, full, c * 64, u0 - 1, T.v0 - 1 + 2 * s, n);
             }
           }
           if (++stage == P.n_stage) { stage = 0; aphase ^= 1; }
         }
       }
     }
+    if (tr && leader) { P.trace[0] = clock64() - tr_t0; P.trace[1] = tr_wait; P.trace[2] = tr_n; P.trace[3] = P.n_stage; }
   } else if (warp == TC_WARP_MMA) {
     // ===================== MMA issuer (pair: the leader CTA only) =====================
     // Runs on the whole warp with warp-uniform control flow; only the issuing instructions are predicated on one elected lane
@@ -253,48 +279,66 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_con
       const bool fp16 = (P.flags & CF_FP16) != 0;
       const uint32_t idesc = make_idesc_f16(PAIR ? 256 : 128, 3 * N, fp16);
       const uint32_t idesc_id = make_idesc_f16(PAIR ? 256 : 128, 64, fp16);
-      const uint64_t adesc128 = ptx::smem_desc_sw128(a_smem, 1024, 0), adesc64 = ptx::smem_desc_sw64(a_smem, 512);
+      const uint64_t adesc128 = ptx::smem_desc_sw128(a_smem + (UPS ? 128u : 0u), 1024, 0), adesc64 = ptx::smem_desc_sw64(a_smem, 512);
       const uint64_t bdesc128 = ptx::smem_desc_sw128(w_smem, 1024, 0), bdesc64 = ptx::smem_desc_sw64(w_smem, 512);
       const uint64_t id_desc = ptx::smem_desc_sw128(id_smem, 1024, 0);
       const uint32_t full0 = ptx::smem_u32(&ctl->a_full[0]), empty0 = ptx::smem_u32(&ctl->a_empty[0]);
       const uint32_t tfull0 = ptx::smem_u32(&ctl->t_full[0]), tempty0 = ptx::smem_u32(&ctl->t_empty[0]);
       int stage = 0;
       uint32_t aphase = 0;
-      int f = 0;            // ring slot of the first block of the group's first input row (even)
-      int pc = 0;           // ring pair this group completes (= f / 2)
-      uint32_t pround = 0;  // parity of that pair's use count
+      uint32_t alloc_par = 0;  // bit p: parity of the NEXT use of ring pair p (both roles count uses of a pair slot from 0)
+      const bool tr = P.trace != nullptr && blockIdx.x == 0;
+      long long tr_full = 0, tr_empty = 0, tr_groups = 0;
+      const long long tr_t0 = tr ? clock64() : 0;
+      // The k-th use of pair slot p may start once the epilogue has drained and cleared use k - 1 (t_empty phase k - 1).
+      auto wait_free = [&](int p) {
+        if (!ptx::mbar_wait_hot(tempty0 + 8 * p, ((alloc_par >> p) & 1u) ^ 1u, wd)) tc_fail(P, 21);
+        alloc_par ^= 1u << p;
+      };
       if (t1 > t0) {
         if (!ptx::mbar_wait_hot(full0, 0, wd)) tc_fail(P, 23);
         ptx::tc_fence_after();
       }
       for (int t = t0; t < t1; t++) {
-        const int ns = (roll_task(Q.tasks, t, 0).rows + 3) >> 1;
+        const RollTaskView T = roll_task(Q.tasks, t, 0);
+        const int ns = (T.rows + 3) >> 1;
+        // rows (v0 - 2, v0 - 1) — the head junk pair — and the segment's first real pair
+        int pc = ((T.v0 + RING - 2) % RING) >> 1;
+        {
+          const long long tw0 = tr ? clock64() : 0;
+          wait_free(pc);
+          wait_free(pc + 1 == NP ? 0 : pc + 1);
+          ptx::tc_fence_after();
+          if (tr) tr_empty += clock64() - tw0;
+        }
         for (int s = 0; s < ns; s++) {
-          const uint32_t col0 = tmem_base + f * N, col1 = col0 + N;
+          const uint32_t col0 = tmem_base + 2 * pc * N, col1 = col0 + N;
           const bool last_group = (t == t1 - 1) && (s == ns - 1);
           for (int c = 0; c < P.n_chunks; c++) {
             const bool half_c = (P.cin - c * 64) < 64;
             const bool last_c = c == P.n_chunks - 1;
-            const uint64_t ad = (half_c ? adesc64 : adesc128) + (uint64_t)(stage * (TC_ASTAGE >> 4));
+            const uint64_t ad = (half_c ? adesc64 : adesc128) + (uint64_t)(stage * (ASTAGE >> 4));
             const uint64_t bd = (half_c ? bdesc64 : bdesc128) + (uint64_t)((c * Q.w_chunk_bytes) >> 4);
             if (half_c) roll_issue_taps<N, PAIR, true, 0, 2>(leader, col0, col1, ad, bd, idesc);
-            else roll_issue_taps<N, PAIR, false, 0, 2>(leader, col0, col1, ad, bd, idesc);
+            else roll_issue_taps<N, PAIR, false, 0, 2, UPS>(leader, col0, col1, ad, bd, idesc);
             // waits for the NEXT stage, hidden behind the MMAs queued above
             int ns_stage = stage + 1;
             uint32_t ns_phase = aphase;
             if (ns_stage == P.n_stage) { ns_stage = 0; ns_phase ^= 1; }
             if (!(last_group && last_c)) {
-              if (last_c) {  // the next group first touches pair (pc + 2) % NP: the epilogue must have drained and cleared it
+              const long long tw0 = tr ? clock64() : 0;
+              if (last_c && s + 1 < ns) {  // the next group of this segment first touches the pair after next
                 int pn = pc + 2;
-                uint32_t rn = pround;
-                if (pn >= NP) { pn -= NP; rn ^= 1; }
-                if (!ptx::mbar_wait_hot(tempty0 + 8 * pn, rn ^ 1, wd)) tc_fail(P, 21);
+                if (pn >= NP) pn -= NP;
+                wait_free(pn);
               }
+              const long long tw1 = tr ? clock64() : 0;
               if (!ptx::mbar_wait_hot(full0 + 8 * ns_stage, ns_phase, wd)) tc_fail(P, 23);
+              if (tr) { tr_empty += tw1 - tw0; tr_full += clock64() - tw1; }
               ptx::tc_fence_after();
             }
             if (half_c) roll_issue_taps<N, PAIR, true, 2, 3>(leader, col0, col1, ad, bd, idesc);
-            else roll_issue_taps<N, PAIR, false, 2, 3>(leader, col0, col1, ad, bd, idesc);
+            else roll_issue_taps<N, PAIR, false, 2, 3, UPS>(leader, col0, col1, ad, bd, idesc);
             if constexpr (N == 64) {
               // split trunk: centre tap of input channels [0, 64) times 5 * I adds the hi half of the residual to the centre rows
               if (P.ident && c == 0 && leader) {
@@ -310,16 +354,21 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_con
             stage = ns_stage;
             aphase = ns_phase;
           }
+          const int pnext = pc + 1 == NP ? 0 : pc + 1;
           if (leader) {
             if constexpr (PAIR) ptx::mma_commit_pair(tfull0 + 8 * pc);
             else ptx::mma_commit(tfull0 + 8 * pc);
+            if (s == ns - 1) {  // the tail junk pair this group first touched: hand it to the epilogue to be cleared
+              if constexpr (PAIR) ptx::mma_commit_pair(tfull0 + 8 * pnext);
+              else ptx::mma_commit(tfull0 + 8 * pnext);
+            }
           }
           __syncwarp();
-          f += 2;
-          if (f == RING) f = 0;
-          if (++pc == NP) { pc = 0; pround ^= 1; }
+          pc = pnext;
+          tr_groups++;
         }
       }
+      if (tr && leader) { P.trace[4] = clock64() - tr_t0; P.trace[5] = tr_full; P.trace[6] = tr_empty; P.trace[7] = tr_groups; }
     }
   } else {
     // ===================== epilogue warps: drain + clear one ring pair per group =====================
@@ -330,15 +379,53 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_con
     const long long run_step = (vert ? (long long)P.w : 1LL) * E.out_stride;  // elements between pixels of a run
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t tempty_leader = PAIR ? ptx::mapa(ptx::smem_u32(&ctl->t_empty[0]), 0) : ptx::smem_u32(&ctl->t_empty[0]);
-    int f = 0, pc = 0;
-    uint32_t pround = 0;
+    uint32_t full_par = 0;  // bit p: parity of the next use of ring pair p
+    const bool tr = P.trace != nullptr && blockIdx.x == 0 && warp == 0;
+    long long tr_wait = 0, tr_work = 0, tr_zero = 0, tr_n = 0;
+    const long long tr_t0 = tr ? clock64() : 0;
     for (int t = t0; t < t1; t++) {
       const RollTaskView T = roll_task(Q.tasks, t, rank);
       const int n = T.n;
       const int u = T.u0 + q * 32 + lane;
       const int ns = (T.rows + 3) >> 1;
-      for (int s = 0; s < ns; s++) {
-        if (!ptx::mbar_wait_wd(ptx::smem_u32(&ctl->t_full[pc]), pround, wd)) tc_fail(P, 31);
+      int pc = ((T.v0 + RING - 2) % RING) >> 1;  // row v lives in slot v % RING; the first pair holds the junk rows v0 - 2, v0 - 1
+      for (int s = 0; s <= ns; s++) {            // ns pairs completed by the segment's groups + its tail junk pair
+        const int f = 2 * pc;
+        // Residual epilogue (rdb.conv5): fetch this warp's residual-1 pieces BEFORE waiting for the accumulators — they do not
+        // depend on the MMAs, and their DRAM latency was most of an iteration (profiles/r02_roll_trace_cfg2s_pair_before_prefetch.txt:
+        // 9 186 cycles per pair against 7 300 of MMA).  Registers hold both 32-channel halves of the 16-bit lo residual, or the
+        // first half of an fp32 residual; everything else is pulled into L2.
+        uint4 pf[8];
+        if constexpr (MODE == EPI_RES) {
+          static_assert(TC_EPI_WARPS == 8, "one row of the pair per epilogue warp");
+          const int o = 2 * s - 2 + rsel, v = T.v0 + o;
+          const bool row_ok = n >= 0 && o >= 0 && o < T.rows && v < v_lim;
+          const int y = vert ? u : v, x = vert ? v : u;
+          const bool valid = row_ok && u < u_lim;
+          const long long fb0 = valid ? f32_index(P.f32, P.h, n, y, x, 0) : 0, lb0 = valid ? lo_index(P.f32, P.h, n, y, x, 0) : 0;
+          if (E.lo_in) {
+            const uint4* r = reinterpret_cast<const uint4*>(E.lo_in + lb0);   // channel c of a pixel: + (c / 8) * 32 pieces
+#pragma unroll
+            for (int i = 0; i < 8; i++) pf[i] = valid ? r[i * 32] : make_uint4(0u, 0u, 0u, 0u);
+          } else {
+            const uint4* r = reinterpret_cast<const uint4*>(E.res1 + fb0);    // channel c of a pixel: + (c / 4) * 32 pieces
+#pragma unroll
+            for (int i = 0; i < 8; i++) pf[i] = valid ? r[i * 32] : make_uint4(0u, 0u, 0u, 0u);
+            if (valid) {  // second half (channels 32..63): 8 pieces x 512 B per warp = 32 lines, one per lane
+              const float* wb = E.res1 + fb0 - (u & 31) * 4 + 8 * 32 * 4;
+              ptx::prefetch_l2(wb + lane * 32);
+            }
+          }
+          if (E.has_res2 && valid) {  // 2 x 32 lines per warp
+            const float* wb = E.res2 + fb0 - (u & 31) * 4;
+            ptx::prefetch_l2(wb + lane * 32);
+            ptx::prefetch_l2(wb + 8 * 32 * 4 + lane * 32);
+          }
+        }
+        const long long te0 = tr ? clock64() : 0;
+        if (!ptx::mbar_wait_wd(ptx::smem_u32(&ctl->t_full[pc]), (full_par >> pc) & 1u, wd)) tc_fail(P, 31);
+        full_par ^= 1u << pc;
+        const long long te1 = tr ? clock64() : 0;
         ptx::tc_fence_after();
         for (int rr_i = rsel; rr_i < 2; rr_i += TC_EPI_WARPS / 4) {
           const int o = 2 * s - 2 + rr_i;  // output row of the segment held by slot f + rr_i
@@ -350,7 +437,7 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_con
           const int y = vert ? u : v, x = vert ? v : u;
           const bool valid = u < u_lim;
           if constexpr (N >= 32) {
-#pragma unroll 1
+#pragma unroll
             for (int c32 = 0; c32 < N / 32; c32++) {
               if (row_ok) {
                 uint32_t rr[32];
@@ -376,7 +463,17 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_con
                   } else {
                     const long long fb = valid ? f32_index(P.f32, P.h, n, y, x, c32 * 32) : 0;
                     const long long lb = valid ? lo_index(P.f32, P.h, n, y, x, c32 * 32) : 0;
-                    epi_res32(E, vv, ctl->bias + c32 * 32, fb, lb, valid, px, run_step, u, u_lim);
+                    float t[32];
+                    if (E.lo_in) {
+                      epi_res_unpack(E, pf + 4 * c32, t);
+                    } else if (c32 == 0) {
+                      epi_res_unpack(E, pf, t);
+                    } else {
+                      uint4 w2[8];
+                      epi_res_fetch(E, fb, lb, valid, w2);
+                      epi_res_unpack(E, w2, t);
+                    }
+                    epi_res32_t(E, vv, t, ctl->bias + c32 * 32, fb, lb, valid, px, run_step, u, u_lim);
                   }
                 }
               }
@@ -405,18 +502,19 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_con
             if (slot < 2) ptx::tmem_st16_zero(maddr);
           }
         }
+        const long long te2 = tr ? clock64() : 0;
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) {
           if constexpr (PAIR) ptx::mbar_arrive_cluster(tempty_leader + 8 * pc);
-          else ptx::mbar_arrive(tempty_leader + 8 * pc);
+          else ptx::mbar_arrive_relaxed(tempty_leader + 8 * pc);
         }
-        f += 2;
-        if (f == RING) f = 0;
-        if (++pc == NP) { pc = 0; pround ^= 1; }
+        if (tr) { tr_wait += te1 - te0; tr_work += te2 - te1; tr_zero += clock64() - te2; tr_n++; }
+        if (++pc == NP) pc = 0;
       }
     }
+    if (tr && lane == 0) { P.trace[8] = clock64() - tr_t0; P.trace[9] = tr_wait; P.trace[10] = tr_work; P.trace[11] = tr_zero; P.trace[12] = tr_n; }
   }
   ptx::tc_fence_before();
   __syncthreads();

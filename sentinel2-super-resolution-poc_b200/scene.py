@@ -148,12 +148,89 @@ class GpuBackend:
         return torch.zeros(self.params.grid ** 2 * 256, dtype=torch.int32, device=self.dev)
 
 
-def run_scene(backend, img, tile, post=True, gather=True, group=None, balance="windows"):
+class DistComm:
+    """The exchanges of ``run_scene`` over ``torch.distributed`` (NCCL on the GPU box, gloo in the CPU tests)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def exchange(self, sends, recvs):
+        """sends: [(tensor, dst)], recvs: [(tensor, src)] — one batched point-to-point round (matched in order per pair)."""
+        ops = [dist.P2POp(dist.isend, t.contiguous(), dst, self.group) for t, dst in sends]
+        ops += [dist.P2POp(dist.irecv, t, src, self.group) for t, src in recvs]
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+    def all_reduce_sum(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def barrier(self):
+        if self.world > 1:
+            dist.barrier(self.group)
+
+
+class ThreadComm:
+    """Same interface for `world` ranks that are THREADS of one process sharing one GPU (each with its own libwowsr handle):
+    lets a single-GPU box run the sharded pipeline — cut tile rows, histogram all-reduce, seam halos, gather — against the
+    single-rank output (tests/test_gpu_scene_ranks.py).  Messages between a pair of ranks are matched in order, like NCCL's."""
+
+    class Shared:
+        def __init__(self, world):
+            import collections
+            import threading
+            self.world = world
+            self.cv = threading.Condition()
+            self.box = collections.defaultdict(collections.deque)   # (src, dst) -> queue of tensors
+            self.red = {}
+            self.red_gen = [0] * world
+            self.bar = threading.Barrier(world)
+
+    def __init__(self, shared, rank):
+        self.s, self.rank, self.world, self.group = shared, rank, shared.world, None
+
+    def exchange(self, sends, recvs):
+        with self.s.cv:
+            for t, dst in sends:
+                self.s.box[(self.rank, dst)].append(t.detach().clone())
+            self.s.cv.notify_all()
+        for t, src in recvs:
+            with self.s.cv:
+                ok = self.s.cv.wait_for(lambda: len(self.s.box[(src, self.rank)]) > 0, timeout=120)
+                if not ok:
+                    raise RuntimeError(f"rank {self.rank}: no message from rank {src}")
+                m = self.s.box[(src, self.rank)].popleft()
+            t.copy_(m)
+
+    def all_reduce_sum(self, t):
+        if torch.cuda.is_available() and t.is_cuda:
+            torch.cuda.current_stream(t.device).synchronize()
+        g = self.s.red_gen[self.rank]
+        self.s.red_gen[self.rank] += 1
+        with self.s.cv:
+            self.s.red.setdefault(g, []).append(t.detach().clone())
+            self.s.cv.notify_all()
+            if not self.s.cv.wait_for(lambda: len(self.s.red[g]) == self.world, timeout=120):
+                raise RuntimeError(f"rank {self.rank}: all-reduce {g} incomplete")
+            parts = list(self.s.red[g])
+        total = parts[0].clone()
+        for q in parts[1:]:
+            total += q
+        t.copy_(total)
+
+    def barrier(self):
+        self.s.bar.wait(timeout=120)
+
+
+def run_scene(backend, img, tile, post=True, gather=True, group=None, balance="windows", comm=None):
     """One pass of the sharded pipeline.  `img`: HxWx3 uint8 tensor on the backend's device (every rank holds
     the LR scene; it is 1/16 of the output).  Returns (plan, local post-processed band, full image on rank 0
-    or None)."""
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    or None).  `comm`: the exchange layer (default: torch.distributed on `group`)."""
+    comm = comm if comm is not None else DistComm(group)
+    world, rank = comm.world, comm.rank
     H, W = img.shape[:2]
     plan = ScenePlan(H, W, tile, world, rank, balance=balance)
     r = backend.blur_radius() if post else 0
@@ -169,16 +246,15 @@ def run_scene(backend, img, tile, post=True, gather=True, group=None, balance="w
     # (1b) tile rows cut between two ranks: ship the SR pieces to the rank that post-processes the row
     mine = [p for p in plan.pieces if p[0] == rank or p[1] == rank]
     if mine:
-        ops, pastes = [], []
+        sends, recvs, pastes = [], [], []
         for (src, dst, y0, y1, x0, x1) in mine:
             if src == rank:
-                ops.append(dist.P2POp(dist.isend, band[y0 - lo:y1 - lo, x0:x1].contiguous(), dst, group))
+                sends.append((band[y0 - lo:y1 - lo, x0:x1].contiguous(), dst))
             else:
                 buf = backend.new_band(y1 - y0, x1 - x0)
-                ops.append(dist.P2POp(dist.irecv, buf, src, group))
+                recvs.append((buf, src))
                 pastes.append((buf, y0, y1, x0, x1))
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
+        comm.exchange(sends, recvs)
         for (buf, y0, y1, x0, x1) in pastes:
             band[y0 - lo:y1 - lo, x0:x1] = buf
     if not post:
@@ -190,22 +266,19 @@ def run_scene(backend, img, tile, post=True, gather=True, group=None, balance="w
             _, _, _, ph = _lib.clahe_geometry(plan.OH, plan.OW, backend.params.grid)
             last = plan.Y1 == plan.OH
             backend.hist(band, plan, lo, plan.Y0, ph if last else plan.Y1, hist)
-        if world > 1:
-            dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+        comm.all_reduce_sum(hist)
         luts = backend.luts(hist, plan)
         # (3) seam halo rows
         if world > 1 and r > 0:
             up, dn = plan.neighbours() if have else (None, None)
-            ops = []
+            sends, recvs = [], []
             if have and up is not None:
-                ops.append(dist.P2POp(dist.isend, band[plan.Y0 - lo:plan.Y0 - lo + r].contiguous(), up, group))
-                ops.append(dist.P2POp(dist.irecv, band[plan.Y0 - r - lo:plan.Y0 - lo], up, group))
+                sends.append((band[plan.Y0 - lo:plan.Y0 - lo + r].contiguous(), up))
+                recvs.append((band[plan.Y0 - r - lo:plan.Y0 - lo], up))
             if have and dn is not None:
-                ops.append(dist.P2POp(dist.isend, band[plan.Y1 - lo - r:plan.Y1 - lo].contiguous(), dn, group))
-                ops.append(dist.P2POp(dist.irecv, band[plan.Y1 - lo:plan.Y1 + r - lo], dn, group))
-            if ops:
-                for req in dist.batch_isend_irecv(ops):
-                    req.wait()
+                sends.append((band[plan.Y1 - lo - r:plan.Y1 - lo].contiguous(), dn))
+                recvs.append((band[plan.Y1 - lo:plan.Y1 + r - lo], dn))
+            comm.exchange(sends, recvs)
         out = backend.new_band(max(plan.Y1 - plan.Y0, 1), plan.OW)
         if have:
             backend.apply(band, plan, lo, luts, out)
@@ -219,11 +292,9 @@ def run_scene(backend, img, tile, post=True, gather=True, group=None, balance="w
             if rank == 0:
                 full = backend.new_band(plan.OH, plan.OW)
                 full[plan.Y0:plan.Y1] = out
-                reqs = [dist.irecv(full[y0:y1], src, group=group) for src, (y0, y1) in enumerate(plan.bands) if src != 0 and y1 > y0]
-                for q in reqs:
-                    q.wait()
+                comm.exchange([], [(full[y0:y1], src) for src, (y0, y1) in enumerate(plan.bands) if src != 0 and y1 > y0])
             elif have:
-                dist.send(out.contiguous(), 0, group=group)
+                comm.exchange([(out.contiguous(), 0)], [])
     return plan, out, full
 
 

@@ -58,15 +58,16 @@ def test_cfg2_full_size_windows_and_oracle(ws):
         w = wins[i]
         alone = _window_alone(up, dimg, w)
         assert torch.equal(full[4 * w.oy0:4 * w.oy1, 4 * w.ox0:4 * w.ox1], alone), i
-    # the shifted corner window against the fp32 oracle
-    w = wins[63]
+    # corner, top edge, interior and the shifted corner window against the fp32 oracle (>= 4 windows)
     torch.set_num_threads(os.cpu_count())
-    ref_f = R.enhance_float(sd, img[w.y0:w.y1, w.x0:w.x1], blocks, 4096)
-    ref = R.quantise(ref_f)[4 * (w.oy0 - w.y0):, 4 * (w.ox0 - w.x0):]
-    got = full[4 * w.oy0:4 * w.oy1, 4 * w.ox0:4 * w.ox1].cpu().numpy()
-    w1, psnr, mx = _metrics(got, ref)
-    print("cfg2 window 63 vs fp32 oracle:", w1, psnr, mx)
-    assert w1 >= 0.999 and psnr >= 50.0, (w1, psnr, mx)
+    for i in (0, 3, 27, 63):
+        w = wins[i]
+        ref_f = R.enhance_float(sd, img[w.y0:w.y1, w.x0:w.x1], blocks, 4096)
+        ref = R.quantise(ref_f)[4 * (w.oy0 - w.y0):4 * (w.oy1 - w.y0), 4 * (w.ox0 - w.x0):4 * (w.ox1 - w.x0)]
+        got = full[4 * w.oy0:4 * w.oy1, 4 * w.ox0:4 * w.ox1].cpu().numpy()
+        w1, psnr, mx = _metrics(got, ref)
+        print(f"cfg2 window {i} vs fp32 oracle:", w1, psnr, mx)
+        assert w1 >= 0.999 and psnr >= 50.0, (i, w1, psnr, mx)
 
 
 def test_cfg5_full_scene_windows(ws):
@@ -83,6 +84,15 @@ def test_cfg5_full_scene_windows(ws):
     for i in (0, 42, 43 * 20 + 21, 1848):
         w = wins[i]
         assert torch.equal(full[4 * w.oy0:4 * w.oy1, 4 * w.ox0:4 * w.ox1], _window_alone(up, dimg, w)), i
+    # corner, interior and shifted-corner windows against the fp32 oracle (276x276: ~10 s of CPU each)
+    torch.set_num_threads(os.cpu_count())
+    for i in (0, 43 * 20 + 21, 1848):
+        w = wins[i]
+        ref_f = R.enhance_float(sd, img[w.y0:w.y1, w.x0:w.x1], blocks, 4096)
+        ref = R.quantise(ref_f)[4 * (w.oy0 - w.y0):4 * (w.oy1 - w.y0), 4 * (w.ox0 - w.x0):4 * (w.ox1 - w.x0)]
+        w1, psnr, mx = _metrics(full[4 * w.oy0:4 * w.oy1, 4 * w.ox0:4 * w.ox1].cpu().numpy(), ref)
+        print(f"cfg5 window {i} vs fp32 oracle:", w1, psnr, mx)
+        assert w1 >= 0.999 and psnr >= 50.0, (i, w1, psnr, mx)
     # determinism of the whole scene (checksum of checksums over row blocks)
     again = up.enhance_cuda(dimg)
     sums = [(int(full[y:y + 4392].to(torch.int64).sum()), int(again[y:y + 4392].to(torch.int64).sum())) for y in range(0, 43920, 4392)]

@@ -131,3 +131,56 @@ def test_full_size_properties_4096(ws, handle):
     a = handle.post_process_host(img, ws._lib.post_params("wow"))
     assert np.array_equal(a, handle.post_process_host(img, ws._lib.post_params("wow")))
     assert np.array_equal(a, wow_cv2.enhance_for_crops(img))
+
+
+def test_clahe_tiles_larger_than_2_pow_24_and_full_chain_stripe(ws, handle):
+    """cfg5's regime: CLAHE tiles of more than 2^24 pixels (32800 = 8 x 4100 -> 16.81 M per tile, clipLimit
+    > 10^5), where cv2's float arithmetic on the clip limit and the uint32 -> float LUT scaling leave the range in which every
+    integer is exact.  Histograms and LUTs bit-exact against the restatement, the CLAHE stage bit-exact against cv2 on the whole
+    1.08 Gpix image, and the full chain (CLAHE -> unsharp -> vegetation boost) bit-exact on a stripe assembled from pinned cv2
+    pieces: cv2 CLAHE on the whole L plane, the rest on the stripe with its blur halo."""
+    import cv2
+    import torch
+    S = 32800
+    small = image_like(S // 4, S // 4, seed=11)
+    img = np.ascontiguousarray(np.repeat(np.repeat(small, 4, 0), 4, 1))
+    del small
+    d = torch.from_numpy(img).cuda()
+    tw, th, pw, ph = ws._lib.clahe_geometry(S, S, 8)
+    assert tw * th > 1 << 24 and (pw, ph) == (S, S)
+    hist = torch.zeros(64 * 256, dtype=torch.int32, device="cuda")
+    luts = torch.zeros(64 * 256, dtype=torch.uint8, device="cuda")
+    im = ws._lib.Image(d.data_ptr(), S * 3, S, S, 0, S)
+    handle.clahe_hist(im, 8, 0, ph, hist.data_ptr())
+    handle.clahe_luts(hist.data_ptr(), 8, tw, th, 2.5, luts.data_ptr())
+    torch.cuda.synchronize()
+    lab = cv2.cvtColor(img, cv2.COLOR_RGB2LAB)
+    L = np.ascontiguousarray(lab[:, :, 0])
+    ref_hist = np.stack([np.stack([np.bincount(L[ty * th:(ty + 1) * th, tx * tw:(tx + 1) * tw].ravel(), minlength=256)
+                                   for tx in range(8)]) for ty in range(8)]).astype(np.uint32)
+    assert np.array_equal(hist.cpu().numpy().astype(np.uint32).reshape(8, 8, 256), ref_hist)
+    ref_luts = P.clahe_luts(ref_hist, tw * th, 2.5)
+    assert np.array_equal(luts.cpu().numpy().reshape(8, 8, 256), ref_luts)
+    # CLAHE stage on the whole image against cv2 itself
+    lab[:, :, 0] = cv2.createCLAHE(clipLimit=2.5, tileGridSize=(8, 8)).apply(L)
+    del L
+    enh = cv2.cvtColor(lab, cv2.COLOR_LAB2RGB)
+    del lab
+    out = torch.empty_like(d)
+    p_clahe = ws._lib.post_params("wow", stages=ws._lib.STAGE_CLAHE)
+    handle.post_process_dev(d.data_ptr(), out.data_ptr(), S, S, p_clahe)
+    torch.cuda.synchronize()
+    for y in range(0, S, 4100):   # compare in slabs: keeps the host copies small
+        assert np.array_equal(out[y:y + 4100].cpu().numpy(), enh[y:y + 4100]), y
+    # full chain on a stripe that crosses a CLAHE tile boundary (rows 4100 * 4 = 16400): the remaining stages are local
+    # (blur radius 3 after zero taps), so cv2 on the stripe plus a 16-row halo reproduces the whole-image result
+    handle.post_process_dev(d.data_ptr(), out.data_ptr(), S, S, ws._lib.post_params("wow"))
+    torch.cuda.synchronize()
+    y0, y1, hl = 16200, 16600, 16
+    e = enh[y0 - hl:y1 + hl]
+    sharp = cv2.addWeighted(e, 1.4, cv2.GaussianBlur(e, (0, 0), 1.2), -0.4, 0)
+    hsv = cv2.cvtColor(sharp, cv2.COLOR_RGB2HSV).astype(np.float32)
+    mask = (hsv[:, :, 0] > 35) & (hsv[:, :, 0] < 85)
+    hsv[:, :, 1] = np.where(mask, np.clip(hsv[:, :, 1] * 1.2, 0, 255), hsv[:, :, 1])
+    ref = cv2.cvtColor(hsv.astype(np.uint8), cv2.COLOR_HSV2RGB)[hl:-hl]
+    assert np.array_equal(out[y0:y1].cpu().numpy(), ref)
