@@ -51,14 +51,20 @@ def wow_sr_array(img_rgb: np.ndarray, upsampler, enhance_crops: bool = True) -> 
 # ---------------------------------------------------------------------------------------------
 
 def normalise_to_uint8_cuda(img: torch.Tensor, eps: float = 0.0) -> torch.Tensor:
-    """The reference's raster normalisation (:66-72) on the device, bit-exact with numpy: rasters whose maximum exceeds
-    255 are min-max stretched in float64 and truncated; everything else is cast (wrapping, like ``astype``).
-    ``eps`` is the ``+ 1e-6`` that ``apply_cnn_sr`` adds to the range (cnn_super_resolution.py:310)."""
+    """The reference's raster normalisation (:66-72) on the device, bit-exact with numpy: rasters whose maximum exceeds 255
+    are min-max stretched and truncated; everything else is cast (wrapping, like ``astype``).  The stretch runs in the type
+    numpy computes it in: float32 rasters in float32, integer and float64 rasters in float64.  A constant raster above 255
+    gives 0/0 = NaN, which numpy's ``astype(uint8)`` turns into 0 (a NaN -> uint8 cast is undefined on CUDA): handled
+    explicitly.  ``eps`` is the ``+ 1e-6`` that ``apply_cnn_sr`` adds to the range (cnn_super_resolution.py:310)."""
     if img.dtype == torch.uint8:
         return img
     mx, mn = img.max(), img.min()
     if float(mx) > 255:
-        return ((img - mn).to(torch.float64) / ((mx - mn).to(torch.float64) + eps) * 255).to(torch.uint8)
+        ft = torch.float32 if img.dtype == torch.float32 else torch.float64
+        rng = (mx - mn).to(ft) + eps
+        if float(rng) == 0.0:
+            return torch.zeros(img.shape, dtype=torch.uint8, device=img.device)
+        return ((img - mn).to(ft) / rng * 255).to(torch.uint8)
     return img.to(torch.int64).to(torch.uint8)
 
 

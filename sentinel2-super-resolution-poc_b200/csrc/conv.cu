@@ -442,8 +442,13 @@ int run_conv_roll(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& 
   const int N = L.N;
   const int64_t roll = wowsr_opt(ctx, "roll", 1);
   if (!roll || (P.flags & (CF_DBG_NO_TMA | CF_DBG_NO_MMA | CF_DBG_NO_STORE))) return 1;
-  if (io.in_ups && (L.cin != 64 || N != 64 || mode != EPI_PLAIN || (io.w & 1) || (io.h & 1) || io.in_C != 64))
-    return wowsr_fail(ctx, WOWSR_ERR_UNSUPPORTED, "folded upsample: 64 -> 64 layers with the plain epilogue at an even resolution only");
+  if (io.in_ups) {  // the folded-upsample instantiation has the plain epilogue only (whatever tc_generic_epilogue says)
+    const bool plain_ok = !io.final && io.out_t && io.out_rep == 1 && !io.out_ps && !io.out_f32_a && !io.out_f32_b && !io.res1 && !io.res2 &&
+                          !io.lo_in && !io.lo_out;
+    if (L.cin != 64 || N != 64 || !plain_ok || (io.w & 1) || (io.h & 1) || io.in_C != 64)
+      return wowsr_fail(ctx, WOWSR_ERR_UNSUPPORTED, "folded upsample: 64 -> 64 layers with the plain epilogue at an even resolution only");
+    mode = EPI_PLAIN;
+  }
   const size_t astage = io.in_ups ? 2 * (size_t)TC_UPS_ROWB : (size_t)TC_ASTAGE;
   bool pair = wowsr_opt(ctx, "roll_pair", 1) != 0 && ctx->sm_count >= 2;
   const size_t id_bytes = P.ident ? (pair ? 4096 : 8192) : 0;
@@ -912,10 +917,16 @@ extern "C" int wowsr_rrdbnet_forward_windows(wowsr_ctx* ctx, const uint8_t* img_
   DeviceGuard g(ctx->device);
   cudaStream_t st = (cudaStream_t)stream;
   const int h = windows[0].y1 - windows[0].y0, w = windows[0].x1 - windows[0].x0;
+  if (pitch < (int64_t)W * 3 || out_pitch < (int64_t)W * 4 * 3 || (out_f32 && out_f32_pitch < (int64_t)W * 4 * 3 * 4))
+    return wowsr_fail(ctx, WOWSR_ERR_ARG, "row pitch smaller than a row (pitch %lld, out_pitch %lld, out_f32_pitch %lld for W = %d)",
+                      (long long)pitch, (long long)out_pitch, (long long)out_f32_pitch, W);
   for (int i = 0; i < n; i++) {
     const wowsr_window& q = windows[i];
     if (q.y1 - q.y0 != h || q.x1 - q.x0 != w || q.x0 < 0 || q.y0 < 0 || q.x1 > W || q.y1 > H)
       return wowsr_fail(ctx, WOWSR_ERR_ARG, "window %d has a different size or lies outside the image", i);
+    // the owned rectangle (may be empty) must lie inside its window: the kernels write it without further checks
+    if (q.ox1 > q.ox0 && q.oy1 > q.oy0 && (q.ox0 < q.x0 || q.ox1 > q.x1 || q.oy0 < q.y0 || q.oy1 > q.y1))
+      return wowsr_fail(ctx, WOWSR_ERR_ARG, "window %d owns pixels outside itself", i);
   }
   // batch size from the workspace budget: 6144 B per LR pixel (data layout)
   int64_t budget = wowsr_opt(ctx, "mem_budget_mb", 49152) << 20;

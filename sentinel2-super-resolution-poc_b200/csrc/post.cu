@@ -582,7 +582,11 @@ extern "C" int wowsr_post_apply(wowsr_ctx* ctx, const wowsr_image* rgb, const ui
   k.sat = p->sat_boost;
   k.inv255 = (float)(1.0 / 255.0);
   k.hscale = (float)(6.0 / 180.0);
-  k.tail_x = rgb->W - rgb->W % 32;
+  // cv2's HSV2RGB_b converts rows in SIMD groups that truncate and finishes each row with a scalar tail that rounds; the
+  // group width is a property of the cv2 BUILD: 32 pixels on the AVX2 builds the goldens come from (opencv-python wheels),
+  // 16 on SSE / NEON builds, 64 on AVX-512 builds.  Option hsv_simd_width selects it (0: no scalar tail).
+  const int simd_w = (int)wowsr_opt(ctx, "hsv_simd_width", 32);
+  k.tail_x = simd_w > 0 ? rgb->W - rgb->W % simd_w : rgb->W;
   if (row0 < 0) row0 = 0;
   if (row1 > rgb->H) row1 = rgb->H;
   if (row0 >= row1) return WOWSR_OK;

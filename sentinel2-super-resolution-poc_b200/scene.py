@@ -192,10 +192,19 @@ class ThreadComm:
     def __init__(self, shared, rank):
         self.s, self.rank, self.world, self.group = shared, rank, shared.world, None
 
+    @staticmethod
+    def _settled(t):
+        """A private copy of `t` that is complete in memory (other threads read it on THEIR streams)."""
+        c = t.detach().clone()
+        if c.is_cuda:
+            torch.cuda.current_stream(c.device).synchronize()
+        return c
+
     def exchange(self, sends, recvs):
+        msgs = [(self._settled(t), dst) for t, dst in sends]
         with self.s.cv:
-            for t, dst in sends:
-                self.s.box[(self.rank, dst)].append(t.detach().clone())
+            for m, dst in msgs:
+                self.s.box[(self.rank, dst)].append(m)
             self.s.cv.notify_all()
         for t, src in recvs:
             with self.s.cv:
@@ -206,12 +215,11 @@ class ThreadComm:
             t.copy_(m)
 
     def all_reduce_sum(self, t):
-        if torch.cuda.is_available() and t.is_cuda:
-            torch.cuda.current_stream(t.device).synchronize()
         g = self.s.red_gen[self.rank]
         self.s.red_gen[self.rank] += 1
+        mine = self._settled(t)
         with self.s.cv:
-            self.s.red.setdefault(g, []).append(t.detach().clone())
+            self.s.red.setdefault(g, []).append(mine)
             self.s.cv.notify_all()
             if not self.s.cv.wait_for(lambda: len(self.s.red[g]) == self.world, timeout=120):
                 raise RuntimeError(f"rank {self.rank}: all-reduce {g} incomplete")

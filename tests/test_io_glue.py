@@ -19,7 +19,7 @@ def _ref_normalise(img):
     return img
 
 
-@pytest.mark.parametrize("case", ["u16_wide", "u16_narrow", "i32_small", "u8"])
+@pytest.mark.parametrize("case", ["u16_wide", "u16_narrow", "i32_small", "u8", "f32_wide", "f64_wide", "u16_constant", "f32_constant"])
 def test_normalise_matches_reference_arithmetic(ws, case):
     """Host logic (runs on CPU tensors too): bit-exact with the reference's numpy expression."""
     rng = np.random.default_rng(11)
@@ -29,9 +29,18 @@ def test_normalise_matches_reference_arithmetic(ws, case):
         a = rng.integers(300, 4000, (20, 33, 3)).astype(np.uint16)
     elif case == "i32_small":
         a = rng.integers(0, 256, (16, 16, 3)).astype(np.uint16)      # max <= 255: plain cast branch
+    elif case == "f32_wide":
+        a = (rng.random((29, 31, 3)) * 9000).astype(np.float32)      # numpy stretches float32 rasters in float32
+    elif case == "f64_wide":
+        a = rng.random((29, 31, 3)) * 9000
+    elif case == "u16_constant":
+        a = np.full((8, 9, 3), 300, np.uint16)                       # 0/0 = NaN -> astype(uint8) gives 0
+    elif case == "f32_constant":
+        a = np.full((8, 9, 3), 300.0, np.float32)
     else:
         a = rng.integers(0, 256, (16, 16, 3)).astype(np.uint8)
-    want = _ref_normalise(a)
+    with np.errstate(all="ignore"):
+        want = _ref_normalise(a)
     t = torch.from_numpy(a.astype(np.int32) if a.dtype == np.uint16 else a)
     got = ws.app.wow_sr.normalise_to_uint8_cuda(t).numpy()
     assert got.dtype == np.uint8 and np.array_equal(got, want)
