@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -50,6 +51,11 @@ struct wowsr_ctx {
   int64_t trace_counter = 0;
   float timing[8] = {0};
   cudaEvent_t ev[8] = {nullptr};
+  // pinned staging ring of the host-buffer entry points (hoststage.h), allocated on first use
+  void* stage[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t stage_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t stage_sync = nullptr;
+  cudaStream_t copy_stream = nullptr;
 };
 
 int wowsr_fail(wowsr_ctx* ctx, int code, const char* fmt, ...);

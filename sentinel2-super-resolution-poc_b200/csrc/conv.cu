@@ -8,6 +8,7 @@
 #include <algorithm>
 
 #include "common.h"
+#include "hoststage.h"
 #include "conv_kernels.cuh"
 #include "ups_kernel.cuh"
 #include "roll_kernel.cuh"
@@ -442,6 +443,7 @@ int run_conv_roll(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& 
   const int N = L.N;
   const int64_t roll = wowsr_opt(ctx, "roll", 1);
   if (!roll || (P.flags & (CF_DBG_NO_TMA | CF_DBG_NO_MMA | CF_DBG_NO_STORE))) return 1;
+  if (io.in_ups && !wowsr_opt(ctx, "roll_ups", 1)) return 1;  // A/B: the tile kernel's folded-upsample variant (ups_kernel.cuh)
   if (io.in_ups) {  // the folded-upsample instantiation has the plain epilogue only (whatever tc_generic_epilogue says)
     const bool plain_ok = !io.final && io.out_t && io.out_rep == 1 && !io.out_ps && !io.out_f32_a && !io.out_f32_b && !io.res1 && !io.res2 &&
                           !io.lo_in && !io.lo_out;
@@ -909,9 +911,10 @@ extern "C" int wowsr_load_rrdbnet(wowsr_ctx* ctx, int32_t num_block, int32_t num
   return WOWSR_OK;
 }
 
-extern "C" int wowsr_rrdbnet_forward_windows(wowsr_ctx* ctx, const uint8_t* img_dev, int32_t H, int32_t W, int64_t pitch,
-                                             const wowsr_window* windows, int32_t n, uint8_t* out_dev, int64_t out_pitch,
-                                             float* out_f32, int64_t out_f32_pitch, void* stream) {
+// `sink` (optional): streams the finished output rows to a host buffer while later batches compute (wowsr_enhance_host).
+static int forward_windows_impl(wowsr_ctx* ctx, const uint8_t* img_dev, int32_t H, int32_t W, int64_t pitch, const wowsr_window* windows,
+                                int32_t n, uint8_t* out_dev, int64_t out_pitch, float* out_f32, int64_t out_f32_pitch, void* stream,
+                                StageOut* sink) {
   if (!ctx || !img_dev || !windows || n < 1 || !out_dev) return WOWSR_ERR_ARG;
   if (!ctx->net || ctx->net->kind != 0) return wowsr_fail(ctx, WOWSR_ERR_STATE, "wowsr_load_rrdbnet has not been called");
   DeviceGuard g(ctx->device);
@@ -935,33 +938,63 @@ extern "C" int wowsr_rrdbnet_forward_windows(wowsr_ctx* ctx, const uint8_t* img_
   int nbatches = (n + maxb - 1) / maxb;
   int per = (n + nbatches - 1) / nbatches;
   float t_head = 0, t_trunk = 0, t_tail = 0;
+  // suffix minimum of the first output row a window owns: after the windows before i are done, no later window writes above it
+  std::vector<int> first_row;
+  if (sink) {
+    first_row.assign(n + 1, 4 * H);
+    for (int i = n - 1; i >= 0; i--) {
+      const wowsr_window& q = windows[i];
+      first_row[i] = (q.ox1 > q.ox0 && q.oy1 > q.oy0) ? std::min(first_row[i + 1], 4 * q.oy0) : first_row[i + 1];
+    }
+  }
+  int sent_rows = 0, final_rows = 0;
   for (int i0 = 0; i0 < n; i0 += per) {
     int nb = std::min(per, n - i0);
     if (int e = rrdbnet_batch(ctx, ctx->net, img_dev, pitch, windows + i0, nb, out_dev, out_pitch, out_f32, out_f32_pitch, st))
       return e;
+    if (sink && final_rows > sent_rows) {  // rows the PREVIOUS batches completed leave while this batch computes
+      sink->enqueue(out_dev, (size_t)out_pitch, sent_rows, final_rows, nullptr);
+      sent_rows = final_rows;
+    }
     if (int e = check_err_flag(ctx, ctx->net, st)) return e;
+    if (sink) final_rows = first_row[i0 + nb];
     float a = 0, b = 0, c = 0;
     cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]);
     cudaEventElapsedTime(&c, ctx->ev[2], ctx->ev[3]);
     t_head += a; t_trunk += b; t_tail += c;
   }
+  if (sink) sink->enqueue(out_dev, (size_t)out_pitch, sent_rows, 4 * H, nullptr);
   ctx->timing[0] = t_head + t_trunk + t_tail;
   ctx->timing[1] = t_head; ctx->timing[2] = t_trunk; ctx->timing[3] = t_tail;
   return WOWSR_OK;
 }
 
-extern "C" int wowsr_enhance_dev(wowsr_ctx* ctx, const uint8_t* img_dev, int32_t H, int32_t W, int32_t tile_size,
-                                 uint8_t* out_dev, float* out_f32_dev, void* stream) {
+extern "C" int wowsr_rrdbnet_forward_windows(wowsr_ctx* ctx, const uint8_t* img_dev, int32_t H, int32_t W, int64_t pitch,
+                                             const wowsr_window* windows, int32_t n, uint8_t* out_dev, int64_t out_pitch,
+                                             float* out_f32, int64_t out_f32_pitch, void* stream) {
+  return forward_windows_impl(ctx, img_dev, H, W, pitch, windows, n, out_dev, out_pitch, out_f32, out_f32_pitch, stream, nullptr);
+}
+
+static int enhance_dev_impl(wowsr_ctx* ctx, const uint8_t* img_dev, int32_t H, int32_t W, int32_t tile_size, uint8_t* out_dev,
+                            float* out_f32_dev, void* stream, StageOut* sink) {
   if (!ctx || H < 1 || W < 1 || tile_size < 1) return WOWSR_ERR_ARG;
   int n = wowsr_plan_windows(H, W, tile_size, 10, nullptr, 0);
   if (n < 1) return wowsr_fail(ctx, WOWSR_ERR_ARG, "planner failed");
   std::vector<wowsr_window> wins(n);
   wowsr_plan_windows(H, W, tile_size, 10, wins.data(), n);
-  return wowsr_rrdbnet_forward_windows(ctx, img_dev, H, W, (int64_t)W * 3, wins.data(), n, out_dev, (int64_t)W * 4 * 3,
-                                       out_f32_dev, (int64_t)W * 4 * 3 * 4, stream);
+  return forward_windows_impl(ctx, img_dev, H, W, (int64_t)W * 3, wins.data(), n, out_dev, (int64_t)W * 4 * 3, out_f32_dev,
+                              (int64_t)W * 4 * 3 * 4, stream, sink);
 }
 
+extern "C" int wowsr_enhance_dev(wowsr_ctx* ctx, const uint8_t* img_dev, int32_t H, int32_t W, int32_t tile_size,
+                                 uint8_t* out_dev, float* out_f32_dev, void* stream) {
+  return enhance_dev_impl(ctx, img_dev, H, W, tile_size, out_dev, out_f32_dev, stream, nullptr);
+}
+
+// Drop-in for RealESRGAN.enhance(img) (cnn_super_resolution.py:217-234) with pageable host buffers.  The input goes up through
+// the pinned ring; the output rows of finished window batches leave through it (copy stream + a few CPU threads) while the
+// following batches compute, so only the last batch's rows are copied after the kernels end.
 extern "C" int wowsr_enhance_host(wowsr_ctx* ctx, const uint8_t* img_host, int32_t H, int32_t W, int32_t tile_size,
                                   uint8_t* out_host, float* out_f32_host) {
   if (!ctx || !img_host || !out_host) return WOWSR_ERR_ARG;
@@ -971,12 +1004,19 @@ extern "C" int wowsr_enhance_host(wowsr_ctx* ctx, const uint8_t* img_host, int32
   if (int e = wowsr_ensure(ctx, ctx->img_out, out_bytes)) return e;
   if (out_f32_host)
     if (int e = wowsr_ensure(ctx, ctx->img_out_f32, out_bytes * 4)) return e;
-  WCUDA(ctx, cudaMemcpyAsync(ctx->img_in.p, img_host, in_bytes, cudaMemcpyHostToDevice, 0));
-  if (int e = wowsr_enhance_dev(ctx, (const uint8_t*)ctx->img_in.p, H, W, tile_size, (uint8_t*)ctx->img_out.p,
-                                out_f32_host ? (float*)ctx->img_out_f32.p : nullptr, nullptr))
+  if (int e = stage_init(ctx)) return e;
+  const size_t row = (size_t)W * 3;
+  if (int e = stage_in(ctx, (uint8_t*)ctx->img_in.p, row, img_host, row, row, H, [](int, int, cudaEvent_t) { return 0; })) return e;
+  WCUDA(ctx, cudaEventRecord(ctx->stage_sync, ctx->copy_stream));
+  WCUDA(ctx, cudaStreamWaitEvent(0, ctx->stage_sync, 0));
+  StageOut sink(ctx, out_host, row * 4, row * 4);
+  if (int e = enhance_dev_impl(ctx, (const uint8_t*)ctx->img_in.p, H, W, tile_size, (uint8_t*)ctx->img_out.p,
+                               out_f32_host ? (float*)ctx->img_out_f32.p : nullptr, nullptr, &sink)) {
+    sink.finish();
     return e;
-  WCUDA(ctx, cudaMemcpyAsync(out_host, ctx->img_out.p, out_bytes, cudaMemcpyDeviceToHost, 0));
+  }
   if (out_f32_host) WCUDA(ctx, cudaMemcpyAsync(out_f32_host, ctx->img_out_f32.p, out_bytes * 4, cudaMemcpyDeviceToHost, 0));
+  if (int e = sink.finish()) return e;
   WCUDA(ctx, cudaStreamSynchronize(0));
   return WOWSR_OK;
 }

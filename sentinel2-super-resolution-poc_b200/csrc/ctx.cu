@@ -5,6 +5,7 @@
 #include <mutex>
 
 #include "common.h"
+#include "hoststage.h"
 
 static thread_local std::string g_create_err;  // last wowsr_create() failure of the calling thread (no ctx to hold it)
 
@@ -248,6 +249,7 @@ extern "C" void wowsr_destroy(wowsr_ctx* ctx) {
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   wowsr_net_free(ctx->net);
   wowsr_net_free(ctx->edsr);
+  stage_free(ctx);
   delete ctx;
 }
 
@@ -258,7 +260,7 @@ extern "C" uint64_t wowsr_launch_count(const wowsr_ctx* ctx) { return ctx ? ctx-
 static const char* const kOptionKeys[] = {
     "conv_impl",   "hist_match", "mem_budget_mb",       "tc_boustrophedon", "tc_chunk32", "tc_flags",
     "tc_force_stream", "tc_generic_epilogue", "tc_grid", "tc_no_strip", "tc_stages", "tc_trace_layer",
-    "tc_wbuf",     "trunk_hilo", "tail_fold_upsample",  "roll", "roll_pair", "roll_grid", "hsv_simd_width"};
+    "tc_wbuf",     "trunk_hilo", "tail_fold_upsample",  "roll", "roll_pair", "roll_grid", "roll_ups", "hsv_simd_width"};
 
 extern "C" int wowsr_set_option(wowsr_ctx* ctx, const char* key, int64_t value) {
   if (!ctx || !key) return WOWSR_ERR_ARG;

@@ -7,6 +7,7 @@
 // FMA contraction, exact fixed-point blur with a single rounding, FMA in HSV->RGB.  All fp32
 // expressions that must round step by step use __fmul_rn/__fadd_rn so -fmad cannot fuse them.
 #include "common.h"
+#include "hoststage.h"
 
 namespace {
 
@@ -649,18 +650,56 @@ extern "C" int wowsr_post_process_dev(wowsr_ctx* ctx, const wowsr_image* rgb, co
   return wowsr_post_apply(ctx, rgb, luts, p, 0, rgb->H, out, stream);
 }
 
+// Drop-in for _enhance_for_crops(img) (wow_sr.py:187-209) with pageable host buffers, pipelined through the pinned ring
+// (hoststage.h): the histogram pass runs on each chunk as it arrives, the apply pass runs per row block and each finished
+// block leaves while the next one is computed.
 extern "C" int wowsr_post_process_host(wowsr_ctx* ctx, const uint8_t* rgb_host, int32_t H, int32_t W,
                                        const wowsr_post_params* p, uint8_t* out_host) {
   if (!ctx || !rgb_host || !out_host || !p || H <= 0 || W <= 0) return WOWSR_ERR_ARG;
   DeviceGuard g(ctx->device);
-  size_t pitch = ((size_t)W * 3 + 15) & ~(size_t)15;
+  const size_t row = (size_t)W * 3;
+  size_t pitch = (row + 15) & ~(size_t)15;
   if (int e = wowsr_ensure(ctx, ctx->post_in, pitch * H)) return e;
   if (int e = wowsr_ensure(ctx, ctx->post_out, pitch * H)) return e;
-  WCUDA(ctx, cudaMemcpy2DAsync(ctx->post_in.p, pitch, rgb_host, (size_t)W * 3, (size_t)W * 3, H, cudaMemcpyHostToDevice, 0));
+  if (int e = stage_init(ctx)) return e;
   wowsr_image in{ctx->post_in.p, (int64_t)pitch, W, H, 0, H};
   wowsr_image out{ctx->post_out.p, (int64_t)pitch, W, H, 0, H};
-  if (int e = wowsr_post_process_dev(ctx, &in, p, &out, nullptr)) return e;
-  WCUDA(ctx, cudaMemcpy2DAsync(out_host, (size_t)W * 3, ctx->post_out.p, pitch, (size_t)W * 3, H, cudaMemcpyDeviceToHost, 0));
+  const bool clahe = (p->stages & WOWSR_STAGE_CLAHE) != 0;
+  int tw = 0, th = 0, pw = 0, ph = 0;
+  if (clahe) {
+    if (p->grid < 1 || p->grid > 64) return wowsr_fail(ctx, WOWSR_ERR_ARG, "bad grid");
+    const int n = p->grid * p->grid * 256;
+    if (int e = wowsr_ensure(ctx, ctx->hist, (size_t)n * 4)) return e;
+    if (int e = wowsr_ensure(ctx, ctx->luts, (size_t)n)) return e;
+    WCUDA(ctx, cudaMemsetAsync(ctx->hist.p, 0, (size_t)n * 4, 0));
+    wowsr_clahe_geometry(H, W, p->grid, &tw, &th, &pw, &ph);
+  }
+  // upload in chunks; pass A on the rows of each chunk as soon as they are on the device (the padded rows below the image
+  // are reflections of rows near the bottom: they go with the last chunk)
+  if (int e = stage_in(ctx, (uint8_t*)ctx->post_in.p, pitch, rgb_host, row, row, H, [&](int r0, int r1, cudaEvent_t ev) -> int {
+        if (cudaStreamWaitEvent(0, ev, 0) != cudaSuccess) return wowsr_fail(ctx, WOWSR_ERR_CUDA, "cudaStreamWaitEvent");
+        if (!clahe) return 0;
+        return wowsr_clahe_hist(ctx, &in, p->grid, r0, r1 == H ? ph : r1, (uint32_t*)ctx->hist.p, nullptr);
+      }))
+    return e;
+  const uint8_t* luts = nullptr;
+  if (clahe) {
+    if (int e = wowsr_clahe_luts(ctx, (const uint32_t*)ctx->hist.p, p->grid, tw, th, p->clip_limit, (uint8_t*)ctx->luts.p, nullptr)) return e;
+    luts = (const uint8_t*)ctx->luts.p;
+  }
+  StageOut sink(ctx, out_host, row, row);
+  int per = (int)std::max<size_t>(1, STAGE_BYTES / row);
+  if (per >= 64) per -= per % 64;  // whole rows of 64 x 64 apply tiles
+  for (int r0 = 0; r0 < H; r0 += per) {
+    const int r1 = std::min(H, r0 + per);
+    if (int e = wowsr_post_apply(ctx, &in, luts, p, r0, r1, &out, nullptr)) {
+      sink.finish();
+      return e;
+    }
+    WCUDA(ctx, cudaEventRecord(ctx->stage_sync, 0));
+    sink.enqueue((const uint8_t*)ctx->post_out.p, pitch, r0, r1, ctx->stage_sync);
+  }
+  if (int e = sink.finish()) return e;
   WCUDA(ctx, cudaStreamSynchronize(0));
   return WOWSR_OK;
 }
