@@ -355,9 +355,11 @@ def run_ours(args):
                 shared = None
         out_host = torch.empty((OH, OW, 3), dtype=torch.uint8).pin_memory() if (rank == 0 and shared is None) else None
 
+        up_bytes = [H * W * 3]
+
         def step_e2e():
             if shared is not None:
-                scene.run_scene_to_host(backend, pinned, tile, shared, post=wl["post"])   # H2D, pipeline, per-rank D2H
+                _, up_bytes[0] = scene.run_scene_to_host(backend, pinned, tile, shared, post=wl["post"])   # H2D, pipeline, per-rank D2H
                 return
             d = pinned.to(dev, non_blocking=True)                       # H2D of this step's input
             _, _, full = scene.run_scene(backend, d, tile, post=wl["post"], gather=True)
@@ -376,10 +378,13 @@ def run_ours(args):
         t_e = torch.tensor([e_ms], device=dev)
         if world > 1:
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-        e2e = {"value": out_mpix / (float(t_e.item()) / 1e3), "unit": "Mpix/s", "h2d_bytes_per_step": int(H * W * 3),
+        t_up = torch.tensor([float(up_bytes[0])], device=dev, dtype=torch.float64)   # bytes uploaded, summed over the ranks
+        if world > 1:
+            dist.all_reduce(t_up, op=dist.ReduceOp.SUM)
+        e2e = {"value": out_mpix / (float(t_e.item()) / 1e3), "unit": "Mpix/s", "h2d_bytes_per_step": int(t_up.item()),
                "d2h_bytes_per_step": int(OH * OW * 3), "ms_per_step": float(t_e.item()),
-               "api": ("RealESRGAN + scene.run_scene_to_host: pinned host input on every rank, every rank copies its band into one "
-                       "shared page-locked host image" if shared is not None else
+               "api": ("RealESRGAN + scene.run_scene_to_host: pinned host input, every rank uploads the LR rows its windows read and copies "
+                       "its band into one shared page-locked host image" if shared is not None else
                        "RealESRGAN + scene.run_scene (enhance -> _enhance_for_crops) with pinned host buffers")}
         if shared is not None:
             shared.close()
@@ -541,7 +546,10 @@ def run_edsr(args):
         t_e = torch.tensor([(time.perf_counter() - t0) / n_e * 1e3], device=dev)
         if world > 1:
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-        e2e = {"value": out_mpix / (float(t_e.item()) / 1e3), "unit": "Mpix/s", "h2d_bytes_per_step": int(H * W * 3),
+        t_up = torch.tensor([float(up_bytes[0])], device=dev, dtype=torch.float64)   # bytes uploaded, summed over the ranks
+        if world > 1:
+            dist.all_reduce(t_up, op=dist.ReduceOp.SUM)
+        e2e = {"value": out_mpix / (float(t_e.item()) / 1e3), "unit": "Mpix/s", "h2d_bytes_per_step": int(t_up.item()),
                "d2h_bytes_per_step": int(48 * H * W), "ms_per_step": float(t_e.item()), "api": "create_sr_model(...)[0].upsample(ndarray) (pageable host arrays)"}
     if rank == 0:
         pk = peaks()

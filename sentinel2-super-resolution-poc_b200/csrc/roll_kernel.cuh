@@ -433,7 +433,23 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_con
         full_par ^= 1u << pc;
         const long long te1 = tr ? clock64() : 0;
         ptx::tc_fence_after();
-        for (int rr_i = rsel; rr_i < 2; rr_i += TC_EPI_WARPS / 4) {
+        // The pair goes back to the issuer as soon as this warp's LAST accumulator block is in registers and cleared — before
+        // the epilogue arithmetic and the stores: the ring then only has to cover the TMEM read, not the store latency (the
+        // three-pair ring of the 64-output layers otherwise couples the MMA stream to the drain time of a pair).
+        long long te2 = 0;
+        auto hand_back = [&]() {
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (PAIR) ptx::mbar_arrive_cluster(tempty_leader + 8 * pc);
+            else ptx::mbar_arrive_relaxed(tempty_leader + 8 * pc);
+          }
+          if (tr) te2 = clock64();
+        };
+        static_assert(TC_EPI_WARPS == 8, "one row of a ring pair per epilogue warp");
+        {
+          const int rr_i = rsel;
           const int o = 2 * s - 2 + rr_i;  // output row of the segment held by slot f + rr_i
           const int slot = f + rr_i;
           const int v = T.v0 + o;
@@ -442,13 +458,46 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_con
           const uint32_t maddr = lane_base + (RING + slot) * N;  // mirror (slots 0 and 1 only)
           const int y = vert ? u : v, x = vert ? v : u;
           const bool valid = u < u_lim;
-          if constexpr (N >= 32) {
+          if constexpr (N == 64 && MODE == EPI_PLAIN) {
+            // both 32-channel halves into registers first, hand the pair back, then the arithmetic of both (two independent
+            // instruction streams for the scheduler to interleave)
+            float va[32], vb[32];
+            if (row_ok) {
+              uint32_t ra[32], rb[32];
+              ptx::tmem_ld32(taddr, ra);
+              ptx::tmem_ld32(taddr + 32, rb);
+              if (slot < 2) {
+                uint32_t ma[32], mb[32];
+                ptx::tmem_ld32(maddr, ma);
+                ptx::tmem_ld32(maddr + 32, mb);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                  va[i] = __fadd_rn(__uint_as_float(ra[i]), __uint_as_float(ma[i]));
+                  vb[i] = __fadd_rn(__uint_as_float(rb[i]), __uint_as_float(mb[i]));
+                }
+              } else {
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; i++) { va[i] = __uint_as_float(ra[i]); vb[i] = __uint_as_float(rb[i]); }
+              }
+            }
+            ptx::tmem_st32_zero(taddr);
+            ptx::tmem_st32_zero(taddr + 32);
+            if (slot < 2) { ptx::tmem_st32_zero(maddr); ptx::tmem_st32_zero(maddr + 32); }
+            hand_back();
+            if (row_ok) {
+              uint16_t* px = E.out_t + (((long long)n * P.h + y) * P.w + x) * E.out_stride;
+              epi_plain32(E, va, ctl->bias, px, run_step, u, u_lim);
+              epi_plain32(E, vb, ctl->bias + 32, px + 32, run_step, u, u_lim);
+            }
+          } else if constexpr (N >= 32) {
 #pragma unroll
             for (int c32 = 0; c32 < N / 32; c32++) {
+              float vv[32];
               if (row_ok) {
                 uint32_t rr[32];
                 ptx::tmem_ld32(taddr + c32 * 32, rr);
-                float vv[32];
                 if (slot < 2) {
                   uint32_t mm[32];
                   ptx::tmem_ld32(maddr + c32 * 32, mm);
@@ -460,6 +509,11 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_con
 #pragma unroll
                   for (int i = 0; i < 32; i++) vv[i] = __uint_as_float(rr[i]);
                 }
+              }
+              ptx::tmem_st32_zero(taddr + c32 * 32);
+              if (slot < 2) ptx::tmem_st32_zero(maddr + c32 * 32);
+              if (c32 == N / 32 - 1) hand_back();
+              if (row_ok) {
                 if constexpr (MODE == EPI_GENERIC) {
                   epilogue_pixel<32, true>(P, n, y, x, c32 * 32, vv, ctl->bias, valid, vert ? (long long)P.w : 1LL, u, u_lim);
                 } else {
@@ -483,14 +537,12 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_con
                   }
                 }
               }
-              ptx::tmem_st32_zero(taddr + c32 * 32);
-              if (slot < 2) ptx::tmem_st32_zero(maddr + c32 * 32);
             }
           } else {
+            float vv[16];
             if (row_ok) {
               uint32_t rr[16];
               ptx::tmem_ld16(taddr, rr);
-              float vv[16];
               if (slot < 2) {
                 uint32_t mm[16];
                 ptx::tmem_ld16(maddr, mm);
@@ -502,21 +554,14 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_con
 #pragma unroll
                 for (int i = 0; i < 16; i++) vv[i] = __uint_as_float(rr[i]);
               }
-              epilogue_pixel<16, true>(P, n, y, x, 0, vv, ctl->bias, valid, vert ? (long long)P.w : 1LL, u, u_lim);
             }
             ptx::tmem_st16_zero(taddr);
             if (slot < 2) ptx::tmem_st16_zero(maddr);
+            hand_back();
+            if (row_ok) epilogue_pixel<16, true>(P, n, y, x, 0, vv, ctl->bias, valid, vert ? (long long)P.w : 1LL, u, u_lim);
           }
         }
-        const long long te2 = tr ? clock64() : 0;
-        ptx::tmem_st_wait();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if constexpr (PAIR) ptx::mbar_arrive_cluster(tempty_leader + 8 * pc);
-          else ptx::mbar_arrive_relaxed(tempty_leader + 8 * pc);
-        }
-        if (tr) { tr_wait += te1 - te0; tr_work += te2 - te1; tr_zero += clock64() - te2; tr_n++; }
+        if (tr) { tr_wait += te1 - te0; tr_work += te2 - te1; tr_zero += clock64() - te2; tr_n++; }  // work = until the hand-back, zero = the rest
         if (++pc == NP) pc = 0;
       }
     }

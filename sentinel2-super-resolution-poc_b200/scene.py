@@ -394,10 +394,30 @@ class SharedHostImage:
             os.unlink(self.path)
 
 
+def lr_rows_needed(H, W, tile, world, rank, balance="windows"):
+    """LR rows [y0, y1) this rank's windows read (every other row of the scene is never touched by its kernels)."""
+    plan = ScenePlan(H, W, tile, world, rank, balance=balance)
+    if not plan.windows:
+        return 0, 0
+    return min(w.y0 for w in plan.windows), max(w.y1 for w in plan.windows)
+
+
 def run_scene_to_host(backend, host_img, tile, shared: SharedHostImage, post=True, balance="windows"):
     """Host-to-host pass: `host_img` (pinned HxWx3 uint8) -> device, sharded pipeline, every rank's band -> `shared`.
-    On return (after the closing barrier) ``shared.array`` holds the complete image in every process."""
-    d = host_img.to(getattr(backend, "dev", "cpu"), non_blocking=True)
+    Each rank uploads only the LR rows its windows read (the ranks' uploads add up to about one copy of the scene).
+    On return (after the closing barrier) ``shared.array`` holds the complete image in every process.  Returns
+    (plan, bytes uploaded by this rank)."""
+    dev = getattr(backend, "dev", "cpu")
+    H, W = host_img.shape[:2]
+    y0, y1 = lr_rows_needed(H, W, tile, shared.world, shared.rank, balance)
+    if shared.world == 1 or (y0, y1) == (0, H):
+        d = host_img.to(dev, non_blocking=True)
+        up_bytes = H * W * 3
+    else:
+        d = torch.empty((H, W, 3), dtype=torch.uint8, device=dev)
+        if y1 > y0:
+            d[y0:y1].copy_(host_img[y0:y1], non_blocking=True)
+        up_bytes = (y1 - y0) * W * 3
     plan, out, _ = run_scene(backend, d, tile, post=post, gather=False, group=shared.group, balance=balance)
     if plan.Y1 > plan.Y0:
         shared.pin_rows(plan.Y0, plan.Y1)
@@ -406,4 +426,4 @@ def run_scene_to_host(backend, host_img, tile, shared: SharedHostImage, post=Tru
         torch.cuda.synchronize()
     if shared.world > 1:
         dist.barrier(shared.group)
-    return plan
+    return plan, up_bytes

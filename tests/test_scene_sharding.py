@@ -122,7 +122,8 @@ def _worker(rank, world, port, H, W, tile, kind, q, balance="windows"):
     img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
     if balance == "shared_host":   # every rank writes its band into one shared host image (no gather on rank 0)
         shared = scene.SharedHostImage(4 * H, 4 * W)
-        plan = scene.run_scene_to_host(OracleBackend(params, ws._lib), torch.from_numpy(img), tile, shared)
+        plan, up_bytes = scene.run_scene_to_host(OracleBackend(params, ws._lib), torch.from_numpy(img), tile, shared)
+        assert 0 <= up_bytes <= img.nbytes
         full = shared.array.clone()
         shared.close()
     else:
