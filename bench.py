@@ -546,11 +546,8 @@ def run_edsr(args):
         t_e = torch.tensor([(time.perf_counter() - t0) / n_e * 1e3], device=dev)
         if world > 1:
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-        t_up = torch.tensor([float(up_bytes[0])], device=dev, dtype=torch.float64)   # bytes uploaded, summed over the ranks
-        if world > 1:
-            dist.all_reduce(t_up, op=dist.ReduceOp.SUM)
-        e2e = {"value": out_mpix / (float(t_e.item()) / 1e3), "unit": "Mpix/s", "h2d_bytes_per_step": int(t_up.item()),
-               "d2h_bytes_per_step": int(48 * H * W), "ms_per_step": float(t_e.item()), "api": "create_sr_model(...)[0].upsample(ndarray) (pageable host arrays)"}
+        e2e = {"value": out_mpix / (float(t_e.item()) / 1e3), "unit": "Mpix/s", "h2d_bytes_per_step": int(H * W * 3) * world,
+               "d2h_bytes_per_step": int(48 * H * W) * world, "ms_per_step": float(t_e.item()), "api": "create_sr_model(...)[0].upsample(ndarray) (pageable host arrays)"}
     if rank == 0:
         pk = peaks()
         conv_t = sum(conv_ms) / len(conv_ms) / 1e3
