@@ -55,6 +55,12 @@ uint64_t wowsr_launch_count(const wowsr_ctx* ctx);
 int wowsr_set_option(wowsr_ctx* ctx, const char* key, int64_t value);
 int wowsr_get_option(const wowsr_ctx* ctx, const char* key, int64_t* value);
 
+/* Copies `rows` rows of `row_bytes` bytes from device memory (ordered after everything queued on `stream`) into a PAGEABLE host
+ * buffer through the handle's pinned staging ring (chunked cudaMemcpyAsync on a copy stream + a few CPU threads); synchronous.
+ * The file entry points use it to bring the finished image down before encoding (server/app/wow_sr.py:126-164). */
+int wowsr_download(wowsr_ctx* ctx, const void* dev, int64_t dev_pitch, int64_t row_bytes, int32_t rows, void* host,
+                   int64_t host_pitch, void* stream);
+
 /* ------------------------------------------------------------------------------------------ */
 /* post-process: wow_sr._enhance_for_crops (server/app/wow_sr.py:187-209) and the farm trio     */
 /* enhance_local_contrast / apply_unsharp_mask / enhance_vegetation as called at                */

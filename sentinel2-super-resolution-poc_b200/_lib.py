@@ -47,6 +47,7 @@ _SIGS = {
     "wowsr_launch_count": (C.c_uint64, [C.c_void_p]),
     "wowsr_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "wowsr_get_option": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]),
+    "wowsr_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "wowsr_post_params_wow": (None, [C.POINTER(PostParams)]),
     "wowsr_post_params_farm": (None, [C.POINTER(PostParams)]),
     "wowsr_clahe_hist": (C.c_int, [C.c_void_p, C.POINTER(Image), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
@@ -163,6 +164,20 @@ class Handle:
         buf = (C.c_int64 * 512)()  # rows 0..63: tile timeline; rows 64..127: epilogue breakdown (instrumented builds)
         n = self._L.wowsr_debug_trace(self._h, buf, 512)
         return np.array(list(buf)[:max(n, 0)], dtype=np.int64).reshape(-1, 4)
+
+    @_locked
+    def download(self, tensor) -> np.ndarray:
+        """A contiguous CUDA tensor -> a new numpy array, through the pinned staging ring (no page-locking of the destination)."""
+        import torch
+        assert tensor.is_cuda and tensor.is_contiguous()
+        out = np.empty(tuple(tensor.shape), dtype=np.dtype(str(tensor.dtype).replace("torch.", "")))
+        rows = int(tensor.shape[0]) if tensor.dim() > 1 else 1
+        row_bytes = tensor.numel() * tensor.element_size() // max(rows, 1)
+        if tensor.numel() == 0:
+            return out
+        self._check(self._L.wowsr_download(self._h, C.c_void_p(tensor.data_ptr()), row_bytes, row_bytes, rows, out.ctypes.data, row_bytes,
+                                           C.c_void_p(torch.cuda.current_stream(tensor.device).cuda_stream)), "download")
+        return out
 
     # -- post-process -------------------------------------------------------------------------
     @_locked

@@ -263,7 +263,7 @@ def apply_cnn_sr(input_path: Path, output_path: Path, scale: int = 4):
         x = wow_sr.normalise_to_uint8_cuda(torch.from_numpy(host).to(model.device), eps=1e-6)
         in_shape = img.shape
         out_bgr = model.enhance_cuda(x.flip(2).contiguous())                # RGB -> BGR (:318-322)
-        output_rgb = out_bgr.flip(2).contiguous().cpu().numpy()
+        output_rgb = wow_sr._to_host(out_bgr.flip(2).contiguous())
         output_bgr = None
     else:
         img = cv2.imread(str(input_path))

@@ -12,7 +12,7 @@ from pathlib import Path
 from typing import Tuple
 
 from .. import _lib
-from .wow_sr import _handle, normalise_to_uint8_cuda, read_image, write_image
+from .wow_sr import _handle, _to_host, normalise_to_uint8_cuda, read_image, write_image
 
 
 def apply_unsharp_mask(img: np.ndarray, strength: float = 1.5, radius: float = 1.0) -> np.ndarray:
@@ -58,7 +58,7 @@ def apply_farm_sr(input_path: Path, output_path: Path, scale: int = 4) -> Tuple[
     x = normalise_to_uint8_cuda(torch.from_numpy(host).to(esrgan.device))
     sr_rgb = esrgan.enhance_cuda(x.flip(2).contiguous()).flip(2).contiguous()
     del esrgan
-    final = farm_post_cuda(sr_rgb).cpu().numpy()
+    final = _to_host(farm_post_cuda(sr_rgb))
     final_output = write_image(final, Path(output_path), transform, crs, scale)
     metadata = {
         "input_file": str(input_path),

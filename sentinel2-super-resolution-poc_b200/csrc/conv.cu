@@ -931,8 +931,10 @@ static int forward_windows_impl(wowsr_ctx* ctx, const uint8_t* img_dev, int32_t 
     if (q.ox1 > q.ox0 && q.oy1 > q.oy0 && (q.ox0 < q.x0 || q.ox1 > q.x1 || q.oy0 < q.y0 || q.oy1 > q.y1))
       return wowsr_fail(ctx, WOWSR_ERR_ARG, "window %d owns pixels outside itself", i);
   }
-  // batch size from the workspace budget: 6144 B per LR pixel (data layout)
-  int64_t budget = wowsr_opt(ctx, "mem_budget_mb", 49152) << 20;
+  // batch size from the workspace budget: 6144 B per LR pixel (data layout).  64 GiB of the 180 GB: a rank of an
+  // 8-GPU cfg5 run (231 windows of 276 x 276) needs two batches instead of three, one GPU 13 instead of 18 — every batch costs
+  // 350 launch prologues and pipeline tails.
+  int64_t budget = wowsr_opt(ctx, "mem_budget_mb", 65536) << 20;
   int64_t per_win = (int64_t)h * w * 6144;
   int maxb = (int)std::max<int64_t>(1, budget / per_win);
   int nbatches = (n + maxb - 1) / maxb;

@@ -253,6 +253,19 @@ extern "C" void wowsr_destroy(wowsr_ctx* ctx) {
   delete ctx;
 }
 
+// Device image -> pageable host buffer through the pinned staging ring (hoststage.h): what the file entry points use to
+// bring the finished image down before encoding it (wow_sr.py:126-164 writes files from a host array).
+extern "C" int wowsr_download(wowsr_ctx* ctx, const void* dev, int64_t dev_pitch, int64_t row_bytes, int32_t rows, void* host,
+                              int64_t host_pitch, void* stream) {
+  if (!ctx || !dev || !host || rows < 1 || row_bytes < 1 || dev_pitch < row_bytes || host_pitch < row_bytes) return WOWSR_ERR_ARG;
+  DeviceGuard g(ctx->device);
+  if (int e = stage_init(ctx)) return e;
+  WCUDA(ctx, cudaEventRecord(ctx->stage_sync, (cudaStream_t)stream));  // everything queued on the producer's stream so far
+  StageOut sink(ctx, (uint8_t*)host, (size_t)host_pitch, (size_t)row_bytes);
+  sink.enqueue((const uint8_t*)dev, (size_t)dev_pitch, 0, rows, ctx->stage_sync);
+  return sink.finish();
+}
+
 extern "C" const char* wowsr_last_error(const wowsr_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 extern "C" uint64_t wowsr_launch_count(const wowsr_ctx* ctx) { return ctx ? ctx->launches : 0; }
 

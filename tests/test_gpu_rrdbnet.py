@@ -268,23 +268,41 @@ def test_kernel_option_paths_agree(ws):
     assert (np.abs(u8.astype(int) - u8_t.astype(int)) <= 1).mean() >= 0.999
     u8_s, f_s = run(conv_impl=1)
     assert np.abs(f - f_s).max() < tol
-    u8_c, f_c = run(tc_chunk32=1)      # rdb.conv5 streamed in 32-channel chunks (other K order, identity K-step per half)
-    assert np.abs(f - f_c).max() < tol and np.abs(f_c - ref_f).max() < 4 * tol
+    # --- the kernels behind the default path's fallbacks: every compiled variant runs and agrees ---
+    # round-1 tile kernel everywhere (conv3x3_tc_kernel + conv3x3_tc_ups_kernel), also with rdb.conv5 streamed in 32-channel chunks
+    for opts in (dict(roll=0), dict(roll=0, tc_chunk32=1), dict(roll=0, tail_fold_upsample=0)):
+        u8_o, f_o = run(**opts)
+        assert np.abs(f - f_o).max() < tol and np.abs(f_o - ref_f).max() < 4 * tol, opts
+        assert (np.abs(u8.astype(int) - u8_o.astype(int)) <= 1).mean() >= 0.999, opts
+    # rolling kernel on single CTAs (rdb.conv5 then falls back to the tile kernel: its weights do not fit one CTA), the tile
+    # kernel's folded-upsample variant under the rolling kernel, producer-side replication
+    for opts in (dict(roll_pair=0), dict(roll_ups=0), dict(tail_fold_upsample=0)):
+        u8_o, f_o = run(**opts)
+        assert np.abs(f - f_o).max() < tol and np.abs(f_o - ref_f).max() < 4 * tol, opts
+        assert (np.abs(u8.astype(int) - u8_o.astype(int)) <= 1).mean() >= 0.999, opts
+    # schedule independence of the rolling kernel: other grids cut the columns elsewhere and walk the ring differently, the
+    # result must not change by a single bit (accumulator slot = row index mod ring size)
+    for units in (2, 3, 20):   # (one unit cannot serve the horizontal and the vertical strip tasks: it would change the geometry)
+        u8_o, f_o = run(roll_grid=units)
+        assert np.array_equal(f, f_o) and np.array_equal(u8, u8_o), units
 
 
 def test_folded_upsample_is_bit_identical_to_replicated_store(ws):
     """conv_up1 / conv_up2 reading the source-resolution buffer through a zero-stride tensor map (the default,
     cnn_super_resolution.py:150-153 folded into the consumer's TMA address generation) see exactly the operands the older
-    producer-side replicated store gives them: outputs must be bit-identical (first hardware run: profiles/r02_queue_fold_upsample.txt)."""
+    producer-side replicated store gives them, in the same order: outputs must be bit-identical — for the rolling kernel and
+    for the round-1 tile kernel (first hardware run: profiles/r02_queue_fold_upsample.txt)."""
     blocks = 1
     sd = R.calibrate_conv_last(R.random_init_state_dict(4, blocks), blocks)
-    for shape, tile in (((150, 276), 256), ((300, 290), 128), ((40, 48), 256)):
-        img = np.random.default_rng(13).integers(0, 256, shape + (3,), dtype=np.uint8)
-        outs = []
-        for fold in (0, 1):
-            h = ws.Handle(0)
-            h.set_option("tail_fold_upsample", fold)
-            h.load_rrdbnet(_tensors(sd, blocks), blocks, precision="bf16")
-            outs.append(h.enhance_host(img, tile, want_float=True))
-            h.close()
-        assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]), (shape, tile)
+    for roll in (1, 0):
+        for shape, tile in (((150, 276), 256), ((300, 290), 128), ((40, 48), 256)):
+            img = np.random.default_rng(13).integers(0, 256, shape + (3,), dtype=np.uint8)
+            outs = []
+            for fold in (0, 1):
+                h = ws.Handle(0)
+                h.set_option("roll", roll)
+                h.set_option("tail_fold_upsample", fold)
+                h.load_rrdbnet(_tensors(sd, blocks), blocks, precision="bf16")
+                outs.append(h.enhance_host(img, tile, want_float=True))
+                h.close()
+            assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]), (roll, shape, tile)
