@@ -147,6 +147,18 @@ int wowsr_green_mask_host(wowsr_ctx* ctx, const uint8_t* rgb_host, int32_t H, in
                           const wowsr_hsv_range* ranges, int32_t n_ranges, float* mask_host);
 
 /* ------------------------------------------------------------------------------------------ */
+/* XYZ tile pyramid: the resampling of gdal2tiles.py --xyz --resampling average                  */
+/* (server/app/tiling.py:147-186) from the device-resident image.  PARITY UNPINNED (no GDAL).     */
+/* ------------------------------------------------------------------------------------------ */
+
+/* Resamples one strip of a zoom level's tile mosaic: mosaic pixel (X, Y) covers the source rectangle
+ * [sx0 + X sxp, sx0 + (X+1) sxp) x [sy0 + Y syp, sy0 + (Y+1) syp) (source pixel units, may lie outside the image).
+ * out: RGBA uint8 [OH][OW][4], alpha 255 where the mosaic pixel's centre is inside the raster (area-weighted mean of the
+ * covered source pixels, rounded half up; nearest pixel when sxp, syp <= 1), 0 elsewhere. */
+int wowsr_tiles_resample(wowsr_ctx* ctx, const wowsr_image* rgb, double sx0, double sy0, double sxp, double syp,
+                         uint8_t* out_rgba_dev, int64_t out_pitch, int32_t OW, int32_t OH, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
 /* window planner: RealESRGAN._tile_process geometry (cnn_super_resolution.py:244-278)         */
 /* ------------------------------------------------------------------------------------------ */
 

@@ -48,6 +48,8 @@ _SIGS = {
     "wowsr_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "wowsr_get_option": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]),
     "wowsr_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
+    "wowsr_tiles_resample": (C.c_int, [C.c_void_p, C.POINTER(Image), C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_int64,
+                                       C.c_int32, C.c_int32, C.c_void_p]),
     "wowsr_post_params_wow": (None, [C.POINTER(PostParams)]),
     "wowsr_post_params_farm": (None, [C.POINTER(PostParams)]),
     "wowsr_clahe_hist": (C.c_int, [C.c_void_p, C.POINTER(Image), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
@@ -178,6 +180,11 @@ class Handle:
         self._check(self._L.wowsr_download(self._h, C.c_void_p(tensor.data_ptr()), row_bytes, row_bytes, rows, out.ctypes.data, row_bytes,
                                            C.c_void_p(torch.cuda.current_stream(tensor.device).cuda_stream)), "download")
         return out
+
+    @_locked
+    def tiles_resample(self, src: Image, sx0, sy0, sxp, syp, out_ptr, out_pitch, OW, OH, stream=0):
+        self._check(self._L.wowsr_tiles_resample(self._h, C.byref(src), float(sx0), float(sy0), float(sxp), float(syp), C.c_void_p(out_ptr),
+                                                 out_pitch, OW, OH, C.c_void_p(stream)), "tiles_resample")
 
     # -- post-process -------------------------------------------------------------------------
     @_locked

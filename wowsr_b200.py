@@ -13,4 +13,5 @@ importlib.import_module("sentinel2-super-resolution-poc_b200.app.wow_sr")
 importlib.import_module("sentinel2-super-resolution-poc_b200.app.farm_sr")
 importlib.import_module("sentinel2-super-resolution-poc_b200.app.vector_extraction")
 importlib.import_module("sentinel2-super-resolution-poc_b200.app.super_resolution")
+importlib.import_module("sentinel2-super-resolution-poc_b200.app.tiling")
 sys.modules[__name__] = _pkg
