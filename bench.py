@@ -34,7 +34,7 @@ sys.path.insert(0, ROOT)
 FLOP_PER_LR_PX = 35_853_696
 EDSR_FLOP_PER_LR_PX = 3_966_336
 POST_BYTES_PER_PX = 9
-TRAFFIC_FILE = "r02_dram_traffic.json"   # written by tools/launch_report.py from the committed ncu launch list
+TRAFFIC_FILES = {532: "r02_dram_traffic.json", 276: "r02_dram_traffic_276.json"}   # by window side; written by tools/launch_report.py from the committed ncu launch lists
 
 
 def peaks():
@@ -433,6 +433,8 @@ def run_ours(args):
         ach = per_rank_flops / conv_t / 1e12
         traffic, traffic_note = None, "not measured on this step"
         try:  # dram__bytes_read+write of the conv launches from the committed ncu launch list (a subset of this workload's windows)
+            wins0 = ws._lib.plan_windows(H, W, tile)
+            TRAFFIC_FILE = TRAFFIC_FILES[wins0[0].x1 - wins0[0].x0]
             with open(os.path.join(ROOT, "profiles", TRAFFIC_FILE)) as f:
                 t = json.load(f)
             traffic = t["dram_bytes"] / (t["windows"] * t.get("side", 532) ** 2) * (flops / world / FLOP_PER_LR_PX)

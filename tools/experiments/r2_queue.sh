@@ -20,23 +20,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O
 ( for mode in 0 1 2 3; do for n in 32 64 96 128 192; do timeout 60 build/mma_ws_bench $mode $n || echo "mode=$mode N=$n exit $?"; done; done ) > $O/r2_mma_ws_bench.txt 2>&1
 ( for n in 32 64 96 128 192; do timeout 60 build/mma_2cta_bench $n || echo "N=$n exit $?"; done ) > $O/r2_mma_2cta_bench.txt 2>&1
 timeout 30 build/tma_stride0_probe > $O/r2_tma_stride0_probe.txt 2>&1; echo "exit $?" >> $O/r2_tma_stride0_probe.txt
-timeout 150 python tools/try_fused.py fold > $O/r2_fold_upsample.txt 2>&1; echo "exit $?" >> $O/r2_fold_upsample.txt
+# (the steps that drove the fused conv4+conv5 launch, the dataflow trunk and the opt-in pytest forms were removed with those kernels
+#  after this queue had measured them: profiles/r02_queue_fused_*.txt, r02_queue_dram_compare.txt, r02_queue_fold_upsample.txt)
 timeout 120 python -m pytest tests/test_zz_gpu_green_mask.py -x -q -m gpu > $O/r2_green_mask_pytest.txt 2>&1
-timeout 150 python tools/try_fused.py check > $O/r2_fused_check.txt 2>&1; echo "exit $?" >> $O/r2_fused_check.txt
-if grep -q "exit 0" $O/r2_fused_check.txt; then
-  timeout 150 python tools/try_fused.py perf 4 0 > $O/r2_fused_perf.txt 2>&1; echo "exit $?" >> $O/r2_fused_perf.txt
-  timeout 60 python tools/try_fused.py trace 4 0 > $O/r2_fused_trace.txt 2>&1; echo "exit $?" >> $O/r2_fused_trace.txt
-  for fuse in 0 4; do
-    timeout 240 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:'conv3x3_tc|rdb_fused' \
-      --csv --log-file $O/r2_dram_fuse$fuse.csv python tools/try_fused_ncu.py $fuse > $O/r2_dram_fuse$fuse.log 2>&1
-  done
-  python tools/dram_compare.py $O/r2_dram_fuse0.csv $O/r2_dram_fuse4.csv > $O/r2_dram_compare.txt 2>&1
-  # the headline workload under the power cap, both paths back to back (a bench line produced with --opt is an experiment, not a result)
-  timeout 240 python bench.py --no-cpu > $O/r2_bench_cfg2_base.json 2> $O/r2_bench_cfg2_base.err
-  timeout 240 python bench.py --no-cpu --opt trunk_fuse=4 > $O/r2_bench_cfg2_fuse4.json 2> $O/r2_bench_cfg2_fuse4.err
-fi
-# the opt-in pytest forms of the experimental paths (skipped in the regular suite)
-WOWSR_TEST_FUSED=1 WOWSR_TEST_FOLD=1 WOWSR_TEST_DATAFLOW=1 timeout 240 python -m pytest tests/test_gpu_rrdbnet.py -q -m gpu -k experimental > $O/r2_experimental_pytest.txt 2>&1
-# 7. energy attribution of the conv kernel under the power cap (tools/energy_isolation.sh): ms, clock, power, joules per step
-#timeout 300 bash tools/energy_isolation.sh > $O/r2_energy_isolation.txt 2>&1
 echo done

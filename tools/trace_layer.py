@@ -1,4 +1,5 @@
-"""Per-tile timeline (clock64) of CTA 0 for selected conv launches of one cfg2s forward."""
+"""Per-tile timeline (clock64) of CTA 0 for selected conv launches of one cfg2s forward — ROUND-1 TILE KERNEL (option roll=0);
+the rolling kernel's per-role cycle attribution is tools/roll_trace.py."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -11,6 +12,7 @@ import bench
 sd = R.random_init_state_dict(0, 23)
 up = ws.app.cnn_super_resolution.RealESRGAN(device="cuda", tile_size=512, state_dict=sd)
 img = torch.from_numpy(bench.make_lr_image(1200, 1200)).cuda()
+up._h.set_option("roll", 0)
 up.enhance_cuda(img); torch.cuda.synchronize()
 flags = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 up._h.set_option("tc_flags", flags)
