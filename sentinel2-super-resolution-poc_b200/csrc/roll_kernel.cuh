@@ -387,7 +387,7 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_con
     const uint32_t tempty_leader = PAIR ? ptx::mapa(ptx::smem_u32(&ctl->t_empty[0]), 0) : ptx::smem_u32(&ctl->t_empty[0]);
     uint32_t full_par = 0;  // bit p: parity of the next use of ring pair p
     const bool tr = P.trace != nullptr && blockIdx.x == 0 && warp == 0;
-    long long tr_wait = 0, tr_work = 0, tr_zero = 0, tr_n = 0;
+    long long tr_wait = 0, tr_work = 0, tr_zero = 0, tr_n = 0, tr_math = 0, tr_store = 0;
     const long long tr_t0 = tr ? clock64() : 0;
     for (int t = t0; t < t1; t++) {
       const RollTaskView T = roll_task(Q.tasks, t, rank);
@@ -519,7 +519,21 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_con
                 } else {
                   uint16_t* px = E.out_t + (((long long)n * P.h + y) * P.w + x) * E.out_stride + c32 * 32;
                   if constexpr (MODE == EPI_PLAIN) {
-                    epi_plain32(E, vv, ctl->bias + c32 * 32, px, run_step, u, u_lim);
+                    if (tr) {  // traced warp only: the same arithmetic with a time stamp between the math and the stores
+                      epi_bias32(vv, ctl->bias + c32 * 32);
+                      if (E.do_act) {
+#pragma unroll
+                        for (int i = 0; i < 32; i++) vv[i] = fmaxf(vv[i], __fmul_rn(vv[i], E.slope));
+                      }
+                      uint32_t pk[16];
+                      epi_pack16(vv, E.out_fp16, pk);
+                      const long long tm = clock64();
+                      epi_store_quad(pk, px, run_step, u, u_lim);
+                      tr_math += tm - te2;
+                      tr_store += clock64() - tm;
+                    } else {
+                      epi_plain32(E, vv, ctl->bias + c32 * 32, px, run_step, u, u_lim);
+                    }
                   } else {
                     const long long fb = valid ? f32_index(P.f32, P.h, n, y, x, c32 * 32) : 0;
                     const long long lb = valid ? lo_index(P.f32, P.h, n, y, x, c32 * 32) : 0;
@@ -565,7 +579,10 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_con
         if (++pc == NP) pc = 0;
       }
     }
-    if (tr && lane == 0) { P.trace[8] = clock64() - tr_t0; P.trace[9] = tr_wait; P.trace[10] = tr_work; P.trace[11] = tr_zero; P.trace[12] = tr_n; }
+    if (tr && lane == 0) {
+      P.trace[8] = clock64() - tr_t0; P.trace[9] = tr_wait; P.trace[10] = tr_work; P.trace[11] = tr_zero; P.trace[12] = tr_n;
+      P.trace[13] = tr_math; P.trace[14] = tr_store;
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();

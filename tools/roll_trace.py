@@ -31,7 +31,7 @@ for layer, name in [(11, "rdb.conv1"), (12, "rdb.conv2"), (14, "rdb.conv4"), (10
     torch.cuda.synchronize()
     t = h.debug_trace().reshape(-1)
     h.set_option("tc_trace_layer", 0)
-    prod, issue, epi = t[0:4], t[4:8], t[8:13]
+    prod, issue, epi = t[0:4], t[4:8], t[8:15]
     if issue[3] == 0:
         print(f"== {name} (launch {layer}): no rolling trace (tile kernel?)")
         continue
@@ -39,5 +39,7 @@ for layer, name in [(11, "rdb.conv1"), (12, "rdb.conv2"), (14, "rdb.conv4"), (10
     print(f"== {name} (launch {layer}): {int(g)} groups (2 input rows each), {int(prod[3])} stages")
     print(f"   issuer   : {issue[0] / g:8.0f} cyc/group total; waiting for TMA data {issue[1] / g:7.0f}, waiting for a free accumulator pair {issue[2] / g:7.0f}")
     print(f"   producer : {prod[0] / g:8.0f} cyc/group total; waiting for a free stage {prod[1] / g:7.0f}  ({int(prod[2])} boxes)")
-    print(f"   epilogue : {epi[0] / g:8.0f} cyc/group total; waiting for accumulators {epi[1] / g:7.0f}, drain + math + stores {epi[2] / g:7.0f}, "
-          f"clear + hand back {epi[3] / g:7.0f}  ({int(epi[4])} pairs)")
+    print(f"   epilogue : {epi[0] / g:8.0f} cyc/group total; waiting for accumulators {epi[1] / g:7.0f}, TMEM read + clear + hand-back {epi[2] / g:7.0f}, "
+          f"arithmetic + stores after the hand-back {epi[3] / g:7.0f}  ({int(epi[4])} pairs)")
+    if epi[5] or epi[6]:
+        print(f"              plain N = 32 epilogue of the traced warp: bias / activation / pack {epi[5] / g:7.0f}, transpose + stores {epi[6] / g:7.0f} cyc/pair")
