@@ -12,6 +12,19 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
+@pytest.fixture(autouse=True, params=["march", "tile"])
+def post_kernel(request, ws, handle):
+    """Every test of this module runs on both compiled pass-B kernels: the strip-march kernel (default) and the
+    round-1 tile kernel (option post_kernel=0)."""
+    v = 1 if request.param == "march" else 0
+    handles = [handle, ws._lib.default_handle(0)]
+    for h in handles:
+        h.set_option("post_kernel", v)
+    yield request.param
+    for h in handles:
+        h.set_option("post_kernel", 1)
+
+
 def test_goldens_from_reference(ws, handle):
     g = np.load(os.path.join(GOLD, "post_wow_96x128.npz"))
     assert np.array_equal(ws.app.wow_sr._enhance_for_crops(g["img"]), g["out"])
@@ -48,12 +61,19 @@ def test_clahe_hist_and_luts_bit_exact(ws, handle, shape):
     hist = torch.zeros(64 * 256, dtype=torch.int32, device="cuda")
     luts = torch.zeros(64 * 256, dtype=torch.uint8, device="cuda")
     im = ws._lib.Image(d.data_ptr(), W * 3, W, H, 0, H)
-    handle.clahe_hist(im, 8, 0, ph, hist.data_ptr())
-    handle.clahe_luts(hist.data_ptr(), 8, tw, th, 2.5, luts.data_ptr())
-    torch.cuda.synchronize()
     L = P.rgb2l_u8(img)
     ref_hist = P.clahe_hist(L, 8)
-    assert np.array_equal(hist.cpu().numpy().astype(np.uint32).reshape(8, 8, 256), ref_hist)
+    for variant in (0, 1, 2):            # every compiled histogram update: one-bin shortcut, match_any grouping, plain atomics (default)
+        hist.zero_()
+        handle.set_option("hist_match", variant)
+        try:
+            handle.clahe_hist(im, 8, 0, ph, hist.data_ptr())
+        finally:
+            handle.set_option("hist_match", 2)
+        torch.cuda.synchronize()
+        assert np.array_equal(hist.cpu().numpy().astype(np.uint32).reshape(8, 8, 256), ref_hist), f"hist_match={variant}"
+    handle.clahe_luts(hist.data_ptr(), 8, tw, th, 2.5, luts.data_ptr())
+    torch.cuda.synchronize()
     assert np.array_equal(luts.cpu().numpy().reshape(8, 8, 256), P.clahe_luts(ref_hist, tw * th, 2.5))
     assert int(hist.sum()) == pw * ph
 
@@ -184,3 +204,52 @@ def test_clahe_tiles_larger_than_2_pow_24_and_full_chain_stripe(ws, handle):
     hsv[:, :, 1] = np.where(mask, np.clip(hsv[:, :, 1] * 1.2, 0, 255), hsv[:, :, 1])
     ref = cv2.cvtColor(hsv.astype(np.uint8), cv2.COLOR_HSV2RGB)[hl:-hl]
     assert np.array_equal(out[y0:y1].cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("nt,seg", [(64, 8), (64, 1), (96, 37), (256, 256), (128, 5)])
+def test_march_kernel_any_strip_and_segment_geometry(ws, handle, post_kernel, nt, seg):
+    """Strip-march kernel with forced strip widths (threads per CTA) and segment heights: many strips and segments on a
+    small image, segments shorter than the blur radius, a partial last strip, one strip wider than the image."""
+    if post_kernel != "march":
+        pytest.skip("geometry options belong to the strip-march kernel")
+    img = image_like(333, 1001, seed=5)
+    handle.set_option("post_nt", nt)
+    handle.set_option("post_seg", seg)
+    try:
+        assert np.array_equal(handle.post_process_host(img, ws._lib.post_params("wow")), wow_cv2.enhance_for_crops(img))
+        assert np.array_equal(handle.post_process_host(img, ws._lib.post_params("farm")), wow_cv2.farm_post(img))
+        big = ws._lib.post_params("farm", sigma=2.0)                       # radius 6 -> the 8-column halo instantiation
+        assert np.array_equal(handle.post_process_host(img, big),
+                              wow_cv2.post_process(img, clip=2.5, grid=8, sigma=2.0, alpha=2.2, beta=-1.2, sat=1.3))
+    finally:
+        handle.set_option("post_nt", 0)
+        handle.set_option("post_seg", 0)
+
+
+def test_unaligned_pitch_and_stage_subsets(ws, handle):
+    """Device entry point on a packed image whose row size is not a multiple of 4 (byte loads / stores instead of 32-bit
+    ones), and every subset of the three stages."""
+    import torch
+    H, W = 203, 301
+    img = image_like(H, W, seed=13)
+    d = torch.from_numpy(img).cuda()
+    out = torch.zeros_like(d)
+    handle.post_process_dev(d.data_ptr(), out.data_ptr(), H, W, ws._lib.post_params("wow"))
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), wow_cv2.enhance_for_crops(img))
+    import cv2
+    for stages in range(1, 8):
+        want = img
+        if stages & 1:
+            lab = cv2.cvtColor(want, cv2.COLOR_RGB2LAB)
+            lab[:, :, 0] = cv2.createCLAHE(clipLimit=2.5, tileGridSize=(8, 8)).apply(lab[:, :, 0])
+            want = cv2.cvtColor(lab, cv2.COLOR_LAB2RGB)
+        if stages & 2:
+            want = cv2.addWeighted(want, 1.4, cv2.GaussianBlur(want, (0, 0), 1.2), -0.4, 0)
+        if stages & 4:
+            hsv = cv2.cvtColor(want, cv2.COLOR_RGB2HSV).astype(np.float32)
+            mask = (hsv[:, :, 0] > 35) & (hsv[:, :, 0] < 85)
+            hsv[:, :, 1] = np.where(mask, np.clip(hsv[:, :, 1] * 1.2, 0, 255), hsv[:, :, 1])
+            want = cv2.cvtColor(hsv.astype(np.uint8), cv2.COLOR_HSV2RGB)
+        got = handle.post_process_host(img, ws._lib.post_params("wow", stages=stages))
+        assert np.array_equal(got, want), f"stages={stages}"
