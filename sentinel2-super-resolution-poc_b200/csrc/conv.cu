@@ -290,7 +290,7 @@ struct LayerIO {
   int ident = 0;
   void* out_t = nullptr;
   int out_stride = 0, out_choff = 0, out_rep = 1;
-  int out_ps = 0;
+  long long out_row = 0;  // elements between output rows, 0: w * out_stride (rolling kernel, plain epilogue)
   int in_ups = 0;  // `in` is at HALF the layer resolution, the nearest-x2 upsample is folded into the tensor maps
   float final_scale = 255.0f;
   float final_add[3] = {0.0f, 0.0f, 0.0f};
@@ -445,7 +445,7 @@ int run_conv_roll(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& 
   if (!roll || (P.flags & (CF_DBG_NO_TMA | CF_DBG_NO_MMA | CF_DBG_NO_STORE))) return 1;
   if (io.in_ups && !wowsr_opt(ctx, "roll_ups", 1)) return 1;  // A/B: the tile kernel's folded-upsample variant (ups_kernel.cuh)
   if (io.in_ups) {  // the folded-upsample instantiation has the plain epilogue only (whatever tc_generic_epilogue says)
-    const bool plain_ok = !io.final && io.out_t && io.out_rep == 1 && !io.out_ps && !io.out_f32_a && !io.out_f32_b && !io.res1 && !io.res2 &&
+    const bool plain_ok = !io.final && io.out_t && io.out_rep == 1 && !io.out_f32_a && !io.out_f32_b && !io.res1 && !io.res2 &&
                           !io.lo_in && !io.lo_out;
     if (L.cin != 64 || N != 64 || !plain_ok || (io.w & 1) || (io.h & 1) || io.in_C != 64)
       return wowsr_fail(ctx, WOWSR_ERR_UNSUPPORTED, "folded upsample: 64 -> 64 layers with the plain epilogue at an even resolution only");
@@ -586,7 +586,7 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
   P.out_f32_a = io.out_f32_a; P.out_f32_b = io.out_f32_b;
   P.out_t = io.out_t; P.out_stride = io.out_stride; P.out_choff = io.out_choff; P.out_rep = io.out_rep;
   P.f32 = io.f32;
-  P.out_ps = io.out_ps; P.final_scale = io.final_scale; P.final_round = io.final_round;
+  P.out_row = io.out_row; P.final_scale = io.final_scale; P.final_round = io.final_round;
   for (int i = 0; i < 3; i++) P.final_add[i] = io.final_add[i];
   P.final = io.final; P.out_u8 = io.out_u8; P.out_u8_pitch = io.out_u8_pitch;
   P.out_img_f32 = io.out_img_f32; P.out_img_f32_pitch = io.out_img_f32_pitch; P.wins = io.wins;
@@ -601,6 +601,8 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
     }
   }
 
+  if (io.out_row && (wowsr_opt(ctx, "conv_impl", 0) == 1 || wowsr_opt(ctx, "tc_generic_epilogue", 0) || !wowsr_opt(ctx, "roll", 1)))
+    return wowsr_fail(ctx, WOWSR_ERR_UNSUPPORTED, "an output row pitch (EDSR upsampler) needs the rolling kernel's plain epilogue");
   if (wowsr_opt(ctx, "conv_impl", 0) == 1) {
     long long total = (long long)io.Nw * io.h * io.w;
     unsigned blocks = (unsigned)((total + 127) / 128);
@@ -613,13 +615,14 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
   }
   {  // rolling kernel (roll_kernel.cuh) for every layer it can hold the weights of; the tile kernel below is the fallback
     int mode_r = EPI_GENERIC;
-    if (!wowsr_opt(ctx, "tc_generic_epilogue", 0) && N >= 32 && !io.final && io.out_t && io.out_rep == 1 && !io.out_ps && !io.out_f32_b) {
+    if (!wowsr_opt(ctx, "tc_generic_epilogue", 0) && N >= 32 && !io.final && io.out_t && io.out_rep == 1 && !io.out_f32_b) {
       if (!io.res1 && !io.res2 && !io.out_f32_a && !io.lo_in && !io.lo_out) mode_r = EPI_PLAIN;
       else if (N == 64 && io.f32.wpb && (io.res1 != nullptr) != (io.lo_in != nullptr) && (io.out_f32_a || io.lo_out)) mode_r = EPI_RES;
     }
     ConvParams PR = P;
     const int rr = run_conv_roll(ctx, net, L, io, PR, mode_r, st);
     if (rr <= 0) return rr;
+    if (io.out_row) return wowsr_fail(ctx, WOWSR_ERR_UNSUPPORTED, "an output row pitch needs the rolling kernel (layer does not fit it)");
   }
   CUtensorMap tmap, tmap_v, tmap32, tmap_v32;
   if (io.in_ups) {
@@ -677,7 +680,7 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
   }
   size_t smem = (size_t)P.n_stage * P.astage + (size_t)P.n_wbuf * chunk_bytes + id_bytes + SMEM_SLACK;
   if (io.in_ups) {  // folded-upsample kernel (ups_kernel.cuh): plain epilogue only
-    if (P.final || P.res1 || P.res2 || P.out_f32_a || P.out_f32_b || P.lo_in || P.lo_out || P.out_rep != 1 || P.out_ps || !P.out_t)
+    if (P.final || P.res1 || P.res2 || P.out_f32_a || P.out_f32_b || P.lo_in || P.lo_out || P.out_rep != 1 || !P.out_t)
       return wowsr_fail(ctx, WOWSR_ERR_UNSUPPORTED, "folded upsample: plain epilogue only");
     WCUDA(ctx, cudaFuncSetAttribute(conv3x3_tc_ups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
     conv3x3_tc_ups_kernel<<<grid, TC_THREADS, smem, st>>>(tmap, tmap_v, P);
@@ -686,7 +689,7 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
   }
   // epilogue specialisation (conv_kernels.cuh): the generic path handles every other layer shape
   int mode = EPI_GENERIC;
-  if (!wowsr_opt(ctx, "tc_generic_epilogue", 0) && N >= 32 && !P.final && P.out_t && P.out_rep == 1 && !P.out_ps && !P.out_f32_b &&
+  if (!wowsr_opt(ctx, "tc_generic_epilogue", 0) && N >= 32 && !P.final && P.out_t && P.out_rep == 1 && !P.out_f32_b &&
       !(P.flags & CF_DBG_NO_STORE)) {
     if (!P.res1 && !P.res2 && !P.out_f32_a && !P.lo_in && !P.lo_out) mode = EPI_PLAIN;
     else if (N == 64 && P.f32.wpb && (P.res1 != nullptr) != (P.lo_in != nullptr) && (P.out_f32_a || P.lo_out)) mode = EPI_RES;
@@ -1142,17 +1145,16 @@ extern "C" int wowsr_load_edsr(wowsr_ctx* ctx, int32_t num_block, int32_t num_fe
     e = upload_layer(ctx, net->layers.back(), tensors[t], tensors[t + 1], 64, 64, f16);
     t += 2;
   }
-  for (int u = 0; u < 2 && !e; u++) {  // 64 -> 256 + depth-to-space(2), split into 4 groups of 64 permuted channels
+  for (int u = 0; u < 2 && !e; u++) {  // 64 -> 256 + depth-to-space(2): one 64 -> 64 layer per sub-pixel phase s = 2 dy + dx
     const float* w = tensors[t];
     const float* b = tensors[t + 1];
     for (int grp = 0; grp < 4 && !e; grp++) {
       std::vector<float> wg((size_t)64 * 64 * 9), bg(64);
-      for (int s = 0; s < 4; s++)
-        for (int i = 0; i < 16; i++) {
-          const int dst = s * 16 + i, src = (16 * grp + i) * 4 + s;  // PixelShuffle: channel c*4 + s -> (c, sub-pixel s)
-          memcpy(&wg[(size_t)dst * 64 * 9], &w[(size_t)src * 64 * 9], sizeof(float) * 64 * 9);
-          bg[dst] = b[src];
-        }
+      for (int c = 0; c < 64; c++) {
+        const int src = c * 4 + grp;  // PixelShuffle: channel c*4 + s -> (c, sub-pixel s)
+        memcpy(&wg[(size_t)c * 64 * 9], &w[(size_t)src * 64 * 9], sizeof(float) * 64 * 9);
+        bg[c] = b[src];
+      }
       net->layers.emplace_back();
       e = upload_layer(ctx, net->layers.back(), wg.data(), bg.data(), 64, 64, f16);
     }
@@ -1229,17 +1231,20 @@ static int edsr_forward(wowsr_ctx* ctx, ConvNet* net, const uint8_t* img_dev, in
     if (int e = run_conv(ctx, net, net->layers[li++], io, st)) return e;
   }
   WCUDA(ctx, cudaEventRecord(ctx->ev[2], st));
-  for (int grp = 0; grp < 4; grp++) {  // up1: 64 -> 256, depth-to-space -> [2H,2W,64]
-    LayerIO io;
-    io.in = b; io.in_C = 64; io.Nw = 1; io.h = H; io.w = W;
-    io.out_t = net->up1.p; io.out_stride = 64; io.out_choff = 16 * grp; io.out_ps = 1; io.out_fp16 = f16;
-    if (int e = run_conv(ctx, net, net->layers[li++], io, st)) return e;
-  }
-  for (int grp = 0; grp < 4; grp++) {  // up2 -> [4H,4W,64]
-    LayerIO io;
-    io.in = net->up1.p; io.in_C = 64; io.Nw = 1; io.h = 2 * H; io.w = 2 * W;
-    io.out_t = net->hra.p; io.out_stride = 64; io.out_choff = 16 * grp; io.out_ps = 1; io.out_fp16 = f16;
-    if (int e = run_conv(ctx, net, net->layers[li++], io, st)) return e;
+  // Upsampler: conv 64 -> 256 + PixelShuffle(2) as FOUR 64 -> 64 launches, one per sub-pixel phase (dy, dx): each writes all 64
+  // channels (one full 128-byte line) of the output pixels (2y + dy, 2x + dx) through the plain epilogue with a pixel stride
+  // of two pixels and a row pitch of two rows.  (Round 1 grouped by output channel: four launches each wrote a 32-byte
+  // quarter of every line through the generic epilogue: 44 % tensor pipe on these 8 launches, a third of the step.)
+  for (int up = 0; up < 2; up++) {
+    const int hh = up ? 2 * H : H, ww = up ? 2 * W : W;
+    uint16_t* dst = (uint16_t*)(up ? net->hra.p : net->up1.p);
+    for (int grp = 0; grp < 4; grp++) {
+      LayerIO io;
+      io.in = up ? net->up1.p : b; io.in_C = 64; io.Nw = 1; io.h = hh; io.w = ww;
+      io.out_t = dst + ((long long)(grp >> 1) * (2 * ww) + (grp & 1)) * 64;
+      io.out_stride = 128; io.out_row = (long long)4 * ww * 64; io.out_fp16 = f16;
+      if (int e = run_conv(ctx, net, net->layers[li++], io, st)) return e;
+    }
   }
   {  // tail 64 -> 3, + mean, round, saturate
     LayerIO io;

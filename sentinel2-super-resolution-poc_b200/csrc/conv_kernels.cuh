@@ -109,7 +109,8 @@ struct ConvParams {
   float* out_f32_b;
   void* out_t;           // T output, pixel stride out_stride (elements), channel offset out_choff
   int out_stride, out_choff, out_rep;
-  int out_ps;            // 1: depth-to-space(2) store: the chunk's channels are ordered [sub-pixel s][c]; s -> (2y+s/2, 2x+s%2)
+  long long out_row;     // elements between rows of the output (rolling kernel only); 0: w * out_stride.  A row pitch of 2 rows with
+                         // a pixel stride of 2 pixels writes one sub-pixel phase of a depth-to-space(2) output (EDSR upsampler)
   F32Layout f32;         // layout of the fp32 trunk buffers (wpb == 0: plain [pixel][64])
   // Split residual trunk x = hi + lo (rdb.conv5): hi is the 16-bit operand copy in channels [0,64) of the dense buffer
   // (which the next RDB reads anyway), lo = bf16(x - hi) in a warp-blocked 16-bit buffer.  Halves the trunk's HBM
@@ -315,23 +316,6 @@ __device__ __forceinline__ void epilogue_pixel(const ConvParams& P, int n, int y
         pk[i] = *reinterpret_cast<uint32_t*>(&bb);
       }
     }
-    if (P.out_ps) {
-      // depth-to-space: 8 channels (16 B) per sub-pixel in this 32-channel chunk
-      static_assert(NCH == 32 || NCH == 16, "");
-      if constexpr (NCH == 32) {
-        if (valid) {
-#pragma unroll
-          for (int sidx = 0; sidx < 2; sidx++) {
-            const int sp = (ch0 >> 4) + sidx;  // sub-pixel index 0..3 (16 channels each within a 64-channel group)
-            long long opix = ((long long)n * (P.h * 2) + (y * 2 + (sp >> 1))) * (P.w * 2) + (x * 2 + (sp & 1));
-            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(P.out_t) + opix * P.out_stride + P.out_choff);
-            o[0] = make_uint4(pk[8 * sidx], pk[8 * sidx + 1], pk[8 * sidx + 2], pk[8 * sidx + 3]);
-            o[1] = make_uint4(pk[8 * sidx + 4], pk[8 * sidx + 5], pk[8 * sidx + 6], pk[8 * sidx + 7]);
-          }
-        }
-      }
-      return;
-    }
     if (P.flags & CF_DBG_NO_STORE) {  // timing-only: keep the math, drop the stores
       uint32_t xx = 0;
 #pragma unroll
@@ -400,6 +384,7 @@ struct EpiConst {
   float slope, scale1, scale2;
   uint16_t* out_t;        // + channel offset
   long long out_stride;   // elements per pixel
+  long long out_row;      // elements per row
   const float* res1;
   const float* res2;
   float* out_f32;
@@ -417,6 +402,7 @@ __device__ __forceinline__ EpiConst make_epi_const(const ConvParams& P) {
   E.scale2 = P.scale2;
   E.out_t = reinterpret_cast<uint16_t*>(P.out_t) + P.out_choff;
   E.out_stride = P.out_stride;
+  E.out_row = P.out_row ? P.out_row : (long long)P.w * P.out_stride;
   E.res1 = P.res1;
   E.res2 = P.res2;
   E.out_f32 = P.out_f32_a;

@@ -920,19 +920,32 @@ void march_plan(int sm_count, int W, int rows, int rad, int hl, int lut_bytes, i
       const double resident = (double)sm_count * cps * groups;  // work items in flight
       const double warps = cps * groups * nt / 32.0;
       const double starve = warps >= 16 ? 1.0 : std::pow(16.0 / warps, 0.6);
-      for (int n_segs = 1; n_segs <= rows; n_segs++) {
+      auto consider = [&](int n_segs) {
+        if (n_segs < 1) n_segs = 1;
+        if (n_segs > rows) n_segs = rows;
         const int seg = (rows + n_segs - 1) / n_segs;
-        if (seg > PM_MAXSEG) continue;
-        if (force_seg && seg != std::min(force_seg, rows)) {
-          if (seg < force_seg) break;
-          continue;
-        }
+        if (seg > PM_MAXSEG) return false;
         // (the warps of the last strip that lie right of the image leave early, but their group still holds its slot)
         const double waves = std::ceil(strips * (double)n_segs / resident);
         const double cost = waves * cps * groups * nt * (seg + 1.2 * rad + 2.0) * starve;
         if (cost < best) best = cost, *nt_out = nt, *groups_out = groups, *seg_out = seg;
-        if (seg <= 8) break;
+        return true;
+      };
+      if (force_seg) {
+        const int seg = std::max(1, std::min(std::min(force_seg, rows), PM_MAXSEG));
+        consider((rows + seg - 1) / seg);
+        continue;
       }
+      // Only segment counts that fill whole waves can be optimal (more segments in the same number of waves only shorten
+      // them): try the first few wave counts whose segments fit the row-descriptor array; beyond them the warm-up rows
+      // of ever shorter segments only add cost.
+      int tried = 0;
+      for (int w = 1; tried < 3; w++) {
+        const int n_segs = (int)std::min<double>(rows, std::floor(w * resident / strips));
+        if (n_segs >= 1 && consider(n_segs)) tried++;
+        if (n_segs >= rows) break;
+      }
+      consider((rows + PM_MAXSEG - 1) / PM_MAXSEG);  // the fewest, longest segments
     }
   }
 }

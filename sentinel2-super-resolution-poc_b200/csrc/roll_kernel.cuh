@@ -382,7 +382,7 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_con
     const int rsel = warp >> 2;   // which row of the pair (TC_EPI_WARPS = 8: 0 / 1)
     const int u_lim = vert ? P.h : P.w, v_lim = vert ? P.w : P.h;
     const EpiConst E = make_epi_const(P);
-    const long long run_step = (vert ? (long long)P.w : 1LL) * E.out_stride;  // elements between pixels of a run
+    const long long run_step = vert ? E.out_row : E.out_stride;  // elements between pixels of a run
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t tempty_leader = PAIR ? ptx::mapa(ptx::smem_u32(&ctl->t_empty[0]), 0) : ptx::smem_u32(&ctl->t_empty[0]);
     uint32_t full_par = 0;  // bit p: parity of the next use of ring pair p
@@ -487,7 +487,7 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_con
             if (slot < 2) { ptx::tmem_st32_zero(maddr); ptx::tmem_st32_zero(maddr + 32); }
             hand_back();
             if (row_ok) {
-              uint16_t* px = E.out_t + (((long long)n * P.h + y) * P.w + x) * E.out_stride;
+              uint16_t* px = E.out_t + ((long long)n * P.h + y) * E.out_row + (long long)x * E.out_stride;
               epi_plain32(E, va, ctl->bias, px, run_step, u, u_lim);
               epi_plain32(E, vb, ctl->bias + 32, px + 32, run_step, u, u_lim);
             }
@@ -517,7 +517,7 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_con
                 if constexpr (MODE == EPI_GENERIC) {
                   epilogue_pixel<32, true>(P, n, y, x, c32 * 32, vv, ctl->bias, valid, vert ? (long long)P.w : 1LL, u, u_lim);
                 } else {
-                  uint16_t* px = E.out_t + (((long long)n * P.h + y) * P.w + x) * E.out_stride + c32 * 32;
+                  uint16_t* px = E.out_t + ((long long)n * P.h + y) * E.out_row + (long long)x * E.out_stride + c32 * 32;
                   if constexpr (MODE == EPI_PLAIN) {
                     if (tr) {  // traced warp only: the same arithmetic with a time stamp between the math and the stores
                       epi_bias32(vv, ctl->bias + c32 * 32);

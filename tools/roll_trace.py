@@ -1,5 +1,5 @@
 """Cycle attribution of CTA 0 of selected rolling-kernel launches (csrc/roll_kernel.cuh, P.trace) of one forward.
-usage: python tools/roll_trace.py [cfg2s|cfg5s] [key=value ...]"""
+usage: python tools/roll_trace.py [cfg2s|cfg5s|cfg1] [key=value ...]"""
 import os
 import sys
 
@@ -18,7 +18,7 @@ sd = ws.app.cnn_super_resolution.RRDBNet(3, 3, 64, 23, 32, 4).state_dict()
 h = ws.Handle(0)
 for k, v in opts.items():
     h.set_option(k, int(v))
-tile, side = (512, 1200) if which == "cfg2s" else (256, 1280)
+tile, side = {"cfg2s": (512, 1200), "cfg1": (256, 128)}.get(which, (256, 1280))
 up = ws.app.cnn_super_resolution.RealESRGAN(device="cuda", tile_size=tile, state_dict=sd, handle=h)
 img = torch.from_numpy(bench.make_lr_image(side, side)).cuda()
 up.enhance_cuda(img)
