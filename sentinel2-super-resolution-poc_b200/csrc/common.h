@@ -43,6 +43,7 @@ struct wowsr_ctx {
   std::map<std::string, int64_t> opts;
   // post-process scratch
   DevBuf hist, luts, post_in, post_out;
+  int* post_err = nullptr;  // mapped pinned host word: a post-process kernel whose exchange barrier timed out sets it (post.cu)
   // network state
   ConvNet* net = nullptr;
   ConvNet* edsr = nullptr;

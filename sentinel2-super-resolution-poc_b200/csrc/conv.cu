@@ -331,7 +331,19 @@ void roll_plan_build(RollPlanHost& R, int Nw, int h, int w, int strip_x0, bool p
   const int per = pair ? 2 : 1;
   const long long pc_h = ((long long)ch.size() + per - 1) / per, pc_v = ((long long)cv.size() + per - 1) / per;  // (pair-)columns
   const long long cost_h = pc_h * (h + 4), cost_v = pc_v * (rem + 4);
-  const int kMinRows = 8;  // do not cut segments shorter than this (each costs 2 extra input rows + a junk pair)
+  // Do not cut segments shorter than this: each costs 2 extra input rows + a junk pair.  Small launches (fewer than 8 rows per
+  // unit, e.g. one 128 x 128 tile) are bound by the LATENCY of a unit's groups (~2 us each), not by throughput, and the SMs a
+  // longer minimum would leave idle do the extra rows for free: 128 rows over 64 units of 2 rows instead of 13 units of 10
+  // (cfg1: 15.7 -> ~10 us per N = 32 launch).
+  int kMinRows = 8;
+  {
+    const long long total_rows = pc_h * h + pc_v * rem;
+    if (total_rows < (long long)max_units * 8) {
+      long long per_unit = (total_rows + max_units - 1) / max_units;
+      per_unit += per_unit & 1;
+      kMinRows = (int)std::max<long long>(2, std::min<long long>(8, per_unit));
+    }
+  }
   int units_v = 0;
   if (pc_v > 0) {
     units_v = (int)((double)max_units * cost_v / (double)(cost_h + cost_v) + 0.5);

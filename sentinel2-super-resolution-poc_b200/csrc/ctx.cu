@@ -228,6 +228,8 @@ extern "C" int wowsr_create(int device, wowsr_ctx** out) {
   if (e == cudaSuccess)
     e = cudaMemcpy(ctx->d_tables, &wowsr_host_tables(), sizeof(WowsrTables), cudaMemcpyHostToDevice);
   for (int i = 0; i < 8 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->ev[i]);
+  if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->post_err, sizeof(int), cudaHostAllocMapped);
+  if (e == cudaSuccess) *ctx->post_err = 0;
   if (e != cudaSuccess) {
     wowsr_fail(nullptr, WOWSR_ERR_CUDA, "context setup: %s", cudaGetErrorString(e));
     delete ctx;
@@ -245,6 +247,7 @@ extern "C" void wowsr_destroy(wowsr_ctx* ctx) {
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->d_tables) cudaFree(ctx->d_tables);
+  if (ctx->post_err) cudaFreeHost(ctx->post_err);
   for (int i = 0; i < 8; i++)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   wowsr_net_free(ctx->net);

@@ -488,6 +488,7 @@ struct MarchK {
   int in_vec, out_vec;  // 32-bit loads / stores allowed (pitch and base multiples of 4)
   int lut_bytes;        // grid * grid * 256 when the LUTs are staged in shared memory
   uint32_t zero;        // 0, unknown to the compiler (see the first row load in the kernel)
+  int* err;             // mapped host word, set to 1 when a wait on the exchange barrier runs out of polls (never in a correct run)
   uint32_t hw[4][PM_MAXPAIR];  // horizontal pass: for pixel j of the group and window pair k, tap of the even column | tap of
                                // the odd column << 8
   int taps2[2 * (2 * PB_MAXR + 1)];  // taps twice in a row: the vertical pass walks the ring slots in storage order
@@ -662,7 +663,7 @@ post_march_kernel(ImgView img, OutView out, const WowsrTables* __restrict__ tabs
   const uint8_t* lut = LUTS ? s_lut : luts;
   __syncthreads();  // barriers initialised, row descriptors and taps written
   if ((tid >> 5) >= warps_active) return;
-  ptx::mbar_wait(bar_tab, 0);
+  if (!ptx::mbar_wait(bar_tab, 0)) *m.err = 1;
 
   // one row of this thread's four pixels as three packed words (r g b r | g b r g | b r g b)
   auto load_row = [&](int i, uint32_t& w0, uint32_t& w1, uint32_t& w2) {
@@ -769,7 +770,7 @@ post_march_kernel(ImgView img, OutView out, const WowsrTables* __restrict__ tabs
         // exchange e = i - 2 - 2 RAD completes on barrier e & 1 (this thread has already arrived for e + 1: on ONE barrier
         // that phase could complete too and the parity wait for e would never return)
         const uint32_t e = (uint32_t)(i - 2 - 2 * RAD);
-        ptx::mbar_wait(bar_x + 8 * (e & 1u), (e >> 1) & 1u);
+        if (!ptx::mbar_wait(bar_x + 8 * (e & 1u), (e >> 1) & 1u)) *m.err = 1;
         if (emit_ok) {
           const int xb = ((i - 2) & 3) * nt;
           uint32_t P[3][NPAIR];
@@ -957,6 +958,16 @@ int check_image(wowsr_ctx* ctx, const wowsr_image* im, const char* what) {
   return 0;
 }
 
+// A strip-march launch whose exchange barrier ran out of polls (a protocol bug, never seen) has produced garbage: the kernel
+// sets the mapped host word, the next post-process call and the host-buffer entry point (after its final synchronise) fail.
+int post_check_err(wowsr_ctx* ctx) {
+  if (ctx->post_err && *(volatile int*)ctx->post_err) {
+    *ctx->post_err = 0;
+    return wowsr_fail(ctx, WOWSR_ERR_CUDA, "a post-process kernel timed out on its exchange barrier; its output is invalid");
+  }
+  return 0;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -1014,6 +1025,7 @@ extern "C" int wowsr_post_apply(wowsr_ctx* ctx, const wowsr_image* rgb, const ui
                                 const wowsr_post_params* p, int32_t row0, int32_t row1, const wowsr_image* out,
                                 void* stream) {
   if (!ctx || !p) return WOWSR_ERR_ARG;
+  if (int e = post_check_err(ctx)) return e;
   if (int e = check_image(ctx, rgb, "input")) return e;
   if (int e = check_image(ctx, out, "output")) return e;
   if (out->W != rgb->W || out->H != rgb->H) return wowsr_fail(ctx, WOWSR_ERR_ARG, "input/output size mismatch");
@@ -1093,6 +1105,7 @@ extern "C" int wowsr_post_apply(wowsr_ctx* ctx, const wowsr_image* rgb, const ui
   MarchK m;
   memset(&m, 0, sizeof m);
   m.hl = rr == 0 ? 0 : (rr <= 4 ? 4 : 8);
+  m.err = ctx->post_err;  // unified addressing: the mapped host pointer is valid on the device
   m.in_vec = rgb->pitch % 4 == 0 && ((uintptr_t)rgb->data) % 4 == 0;
   m.out_vec = out->pitch % 4 == 0 && ((uintptr_t)out->data) % 4 == 0;
   const bool lut_smem = (p->stages & WOWSR_STAGE_CLAHE) && p->grid <= 8 && ((uintptr_t)luts_dev) % 16 == 0;  // bulk-copy alignment
@@ -1203,7 +1216,7 @@ extern "C" int wowsr_post_process_host(wowsr_ctx* ctx, const uint8_t* rgb_host, 
   }
   if (int e = sink.finish()) return e;
   WCUDA(ctx, cudaStreamSynchronize(0));
-  return WOWSR_OK;
+  return post_check_err(ctx);
 }
 
 extern "C" int wowsr_green_mask(wowsr_ctx* ctx, const wowsr_image* rgb, const wowsr_hsv_range* ranges, int32_t n_ranges,

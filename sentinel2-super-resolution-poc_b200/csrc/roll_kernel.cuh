@@ -148,6 +148,10 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_con
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;
+  // debug (tools/roll_trace.py): phases of CTA 0 in nanoseconds — entry, barriers + TMEM ready, weights resident, roles done, exit
+  const bool tr_ph = P.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  auto tr_now = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (long long)t; };
+  if (tr_ph) P.trace[16] = tr_now();
   const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const bool vert = unit >= Q.units_h;
   const CUtensorMap& tmap = vert ? tmap_v : tmap_h;
@@ -201,6 +205,7 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_con
   if constexpr (PAIR) ptx::cluster_sync();  // the peer's barriers are initialised before anything signals them
   ptx::tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xFFFFFFFFu, ctl->tmem_base, 0);
+  if (tr_ph) P.trace[17] = tr_now();
 
   // ---------------- set-up, phase 2: resident weights, cleared accumulator ring ----------------
   if (warp == TC_WARP_TMA && ptx::elect_one()) {
@@ -222,6 +227,7 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_con
   __syncthreads();
   if constexpr (PAIR) ptx::cluster_sync();  // both CTAs' weight halves are in place before the leader issues
   ptx::tc_fence_after();
+  if (tr_ph) P.trace[18] = tr_now();
 
   if (warp == TC_WARP_TMA) {
     // ===================== TMA producer: one 2-row box per (stage, chunk) =====================
@@ -586,9 +592,11 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_con
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (tr_ph) P.trace[19] = tr_now();
   if constexpr (PAIR) ptx::cluster_sync();  // the peer's shared memory and barriers stay alive until both CTAs are done
   if (warp == TC_WARP_MMA) {
     if constexpr (PAIR) ptx::tmem_dealloc_pair(tmem_base, TMEM_COLS);
     else ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }
+  if (tr_ph) P.trace[20] = tr_now();
 }

@@ -41,5 +41,8 @@ for layer, name in [(11, "rdb.conv1"), (12, "rdb.conv2"), (14, "rdb.conv4"), (10
     print(f"   producer : {prod[0] / g:8.0f} cyc/group total; waiting for a free stage {prod[1] / g:7.0f}  ({int(prod[2])} boxes)")
     print(f"   epilogue : {epi[0] / g:8.0f} cyc/group total; waiting for accumulators {epi[1] / g:7.0f}, TMEM read + clear + hand-back {epi[2] / g:7.0f}, "
           f"arithmetic + stores after the hand-back {epi[3] / g:7.0f}  ({int(epi[4])} pairs)")
+    if len(t) > 20 and t[16]:
+        ph = [int(t[i] - t[16]) for i in range(17, 21)]
+        print(f"   phases of CTA 0 (ns after entry): barriers + TMEM ready {ph[0]}, weights resident {ph[1]}, roles done {ph[2]}, exit {ph[3]}")
     if epi[5] or epi[6]:
         print(f"              plain N = 32 epilogue of the traced warp: bias / activation / pack {epi[5] / g:7.0f}, transpose + stores {epi[6] / g:7.0f} cyc/pair")
