@@ -117,7 +117,38 @@ class RRDBNet(nn.Module):
         return [sd[n + s].cpu().numpy() for n in self._names for s in (".weight", ".bias")]
 
     def forward(self, x):
-        raise NotImplementedError("run the network through RealESRGAN.enhance(); the kernels take uint8 windows")
+        """``RRDBNet.forward`` (cnn_super_resolution.py:139-157): float NCHW in [0, 1] -> float NCHW at 4x, through the CUDA
+        kernels of the ``RealESRGAN`` this module belongs to (``RealESRGAN.model``).  The kernels fuse the ``/ 255`` of
+        ``enhance`` (:220) into the first conv and therefore take inputs ON THE UINT8 GRID (k / 255, what ``enhance`` and
+        ``_tile_process`` feed the model); anything else raises ``ValueError``."""
+        bound = getattr(self, "_wowsr", None)          # (libwowsr handle holding these weights, device): set by RealESRGAN
+        if bound is None:
+            raise RuntimeError("RRDBNet.forward runs through the kernels of a RealESRGAN: use RealESRGAN(...).model(x)")
+        return _forward_float(bound[0], bound[1], x, None)
+
+
+@torch.no_grad()
+def _forward_float(h, device, x: torch.Tensor, tile_size=None) -> torch.Tensor:
+    """Float NCHW on the uint8 grid -> float NCHW pre-quantisation output of the network loaded in handle `h`; untiled
+    (``tile_size=None``) or with the reference's tile / tile_pad stitching."""
+    if x.dim() != 4 or x.shape[1] != 3:
+        raise ValueError("expected a float tensor of shape (N, 3, H, W)")
+    x = x.detach().to(device, torch.float32)
+    q = torch.round(x * 255.0)
+    if not bool(torch.all((q >= 0) & (q <= 255) & (torch.abs(x * 255.0 - q) < 1e-3))):
+        raise ValueError("the CUDA path takes inputs on the uint8 grid (k / 255): the first conv reads uint8 windows")
+    N, _, H, W = x.shape
+    u8 = q.to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+    out = torch.empty((N, 4 * H, 4 * W, 3), dtype=torch.float32, device=device)
+    scratch = torch.empty((4 * H, 4 * W, 3), dtype=torch.uint8, device=device)
+    stream = torch.cuda.current_stream(device).cuda_stream
+    # forward: the whole image is one window; _tile_process: ALWAYS the window table (the h*w > 4 T^2 switch belongs to enhance, :226)
+    wins = [_lib.Window(0, 0, W, H, 0, 0, W, H)] if tile_size is None else _lib.plan_windows(H, W, tile_size, 10)
+    with h.lock:
+        for n in range(N):
+            h.forward_windows(u8[n].data_ptr(), H, W, W * 3, wins, scratch.data_ptr(), 4 * W * 3, dst_f32_ptr=out[n].data_ptr(),
+                              dst_f32_pitch=4 * W * 3 * 4, stream=stream)
+    return out.permute(0, 3, 1, 2)
 
 
 # Loaded-model residency (SURVEY 8f.2).  The reference constructs and deletes a ``RealESRGAN`` per request
@@ -206,6 +237,7 @@ class RealESRGAN:
         self.model.eval()
         self._h = handle if handle is not None else _lib.Handle(dev_index)
         self._h.load_rrdbnet(self.model.tensors(), config["blocks"], config["channels"], 32, precision)
+        self.model._wowsr = (self._h, self.device)
         if key is not None:
             with _cache_lock:
                 _MODEL_CACHE[key] = (self.model, self._h)
@@ -239,8 +271,10 @@ class RealESRGAN:
                                 stream=torch.cuda.current_stream(img.device).cuda_stream)
         return out
 
-    def _tile_process(self, img):  # kept for interface parity; the planner + stitching are native
-        raise NotImplementedError("tiling runs inside libwowsr (wowsr_plan_windows / wowsr_rrdbnet_forward_windows)")
+    def _tile_process(self, img: torch.Tensor) -> torch.Tensor:
+        """``_tile_process`` (:236-280): float (N, 3, H, W) on the uint8 grid -> stitched float output.  The window planner and
+        the last-writer-wins stitching run inside libwowsr (wowsr_plan_windows / wowsr_rrdbnet_forward_windows)."""
+        return _forward_float(self._h, self.device, img, self.tile_size)
 
 
 def apply_cnn_sr(input_path: Path, output_path: Path, scale: int = 4):

@@ -153,6 +153,31 @@ def test_anime_6_block_model_vs_oracle(ws):
         assert np.abs(f - ref_f).max() < 0.02 * max(1.0, np.abs(ref_f).max())
 
 
+def test_model_forward_and_tile_process_vs_oracle(ws):
+    """``RealESRGAN.model(x)`` (RRDBNet.forward, :139-157) and ``RealESRGAN._tile_process(x)`` (:236-280) on float NCHW tensors, the
+    way ``enhance`` calls them (:219-231): against the fp32 oracle, untiled and stitched; off-grid inputs are refused."""
+    import torch
+    blocks = 6
+    sd = R.calibrate_conv_last(R.random_init_state_dict(3, blocks), blocks)
+    up = ws.app.cnn_super_resolution.RealESRGAN(device="cuda", tile_size=32, model_name="realesrgan_anime", state_dict=sd)
+    img = np.random.default_rng(11).integers(0, 256, (2, 70, 90, 3), dtype=np.uint8)
+    x = torch.from_numpy(img).permute(0, 3, 1, 2).float().div(255.0).cuda()
+    y = up.model(x)                                             # one window per image
+    z = up._tile_process(x)                                     # 3 x 3 windows of 52 with the reference's stitching
+    assert y.shape == z.shape == (2, 3, 280, 360) and y.dtype == torch.float32
+    for n in range(2):
+        for got, tile in ((y, 256), (z, 32)):
+            ref_f = R.enhance_float(sd, img[n], blocks, tile)   # tile 256: one window; tile 32: 70 * 90 > 4 * 32^2 -> stitched
+            g = got[n].permute(1, 2, 0).cpu().numpy()
+            assert np.abs(g - ref_f).max() < 0.02 * max(1.0, np.abs(ref_f).max()), (n, tile)
+            w1, psnr, mx = _metrics(R.quantise(g), R.quantise(ref_f))
+            assert w1 >= 0.999 and psnr >= 50.0, (n, tile, w1, psnr, mx)
+    with pytest.raises(ValueError):
+        up.model(x + 0.3 / 255.0)
+    with pytest.raises(RuntimeError):
+        ws.app.cnn_super_resolution.RRDBNet(3, 3, 64, 6, 32, 4)(x)
+
+
 def test_upsampler_surface(ws):
     cnn = ws.app.cnn_super_resolution
     sd = R.random_init_state_dict(0, 6)
