@@ -253,3 +253,12 @@ def test_unaligned_pitch_and_stage_subsets(ws, handle):
             want = cv2.cvtColor(hsv.astype(np.uint8), cv2.COLOR_HSV2RGB)
         got = handle.post_process_host(img, ws._lib.post_params("wow", stages=stages))
         assert np.array_equal(got, want), f"stages={stages}"
+
+
+@pytest.mark.parametrize("grid", [2, 4, 16])
+def test_other_clahe_grids(ws, handle, grid):
+    """CLAHE grids other than 8: up to 8 the LUTs are staged in shared memory, above they are read from global memory
+    (enhance_local_contrast takes grid_size as a parameter, farm_sr.py:61-69)."""
+    img = image_like(517, 403, seed=grid)
+    got = handle.post_process_host(img, ws._lib.post_params("wow", grid=grid))
+    assert np.array_equal(got, wow_cv2.post_process(img, grid=grid))
