@@ -1213,7 +1213,7 @@ static int edsr_forward(wowsr_ctx* ctx, ConvNet* net, const uint8_t* img_dev, in
     F.img = img_dev; F.pitch = (long long)W * 3; F.cin = 3; F.win_xy = (const int*)net->winxy.p;
     F.Nw = 1; F.h = H; F.w = W; F.weight = net->first_w; F.bias = net->first_b;
     F.f32 = fl;
-    F.f32_a = (float*)net->feat.p; F.f32_b = (float*)net->trunk.p;
+    F.f32_a = (float*)net->feat.p;  // the first resblock reads its residual from `feat`: no second fp32 copy of the head's output
     F.out_t = net->dense0.p; F.out_stride = 64; F.out_fp16 = f16; F.in_scale_div = 1.0f;
     for (int i = 0; i < 3; i++) F.sub[i] = kEdsrMean[i];
     dim3 grid((unsigned)((px + 127) / 128), 4);
@@ -1231,7 +1231,7 @@ static int edsr_forward(wowsr_ctx* ctx, ConvNet* net, const uint8_t* img_dev, in
     if (int e = run_conv(ctx, net, net->layers[li++], io, st)) return e;
     LayerIO io2;
     io2.in = b; io2.in_C = 64; io2.Nw = 1; io2.h = H; io2.w = W;
-    io2.f32 = fl; io2.scale1 = net->res_scale; io2.res1 = (const float*)net->trunk.p; io2.out_f32_a = (float*)net->trunk.p;
+    io2.f32 = fl; io2.scale1 = net->res_scale; io2.res1 = (const float*)(blk == 0 ? net->feat.p : net->trunk.p); io2.out_f32_a = (float*)net->trunk.p;
     io2.out_t = a; io2.out_stride = 64; io2.out_fp16 = f16;
     if (int e = run_conv(ctx, net, net->layers[li++], io2, st)) return e;
   }

@@ -1109,8 +1109,12 @@ __global__ void __launch_bounds__(128)
 conv_first_kernel(const FirstParams P) {
   __shared__ float s_w[27 * 64];
   __shared__ float s_b[64];
+  __shared__ float s_in[3][256];  // the normalised input value of every byte, per channel: u8 / div - mean, computed once (27 divisions
+                                  // per thread otherwise: the kernel was bound by them, not by its stores)
   for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) s_w[i] = P.weight[i];
   if (threadIdx.x < 64) s_b[threadIdx.x] = P.bias[threadIdx.x];
+  for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x)
+    s_in[i >> 8][i & 255] = __fsub_rn(__fdiv_rn((float)(i & 255), P.in_scale_div), P.sub[i >> 8]);
   __syncthreads();
   const long long total = (long long)P.Nw * P.h * P.w;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1132,7 +1136,7 @@ conv_first_kernel(const FirstParams P) {
       const uint8_t* ip = P.img + (long long)(wy + yy) * P.pitch + (long long)(wx + xx) * 3;
 #pragma unroll
       for (int ci = 0; ci < 3; ci++) {
-        float a = __fsub_rn(__fdiv_rn((float)ip[ci], P.in_scale_div), P.sub[ci]);
+        const float a = s_in[ci][ip[ci]];
         const float* wr = s_w + ((ky * 3 + kx) * 3 + ci) * 64 + qd * 16;
 #pragma unroll
         for (int co = 0; co < 16; co++) acc[co] = fmaf(a, wr[co], acc[co]);
