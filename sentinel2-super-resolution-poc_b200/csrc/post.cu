@@ -499,6 +499,13 @@ __device__ __forceinline__ uint32_t sat_rn_u8(float x) {
   asm("cvt.rni.u8.f32 %0, %1;" : "=r"(r) : "f"(x));  // round to nearest even, saturate to [0, 255]: one F2IP
   return r;
 }
+// unsigned -> float through the 32-bit conversion (I2FP, ALU pipe); the compiler turns conversions of values it knows to be
+// 16-bit into I2F.U16 on the quarter-rate XU pipe (12 per pixel in this kernel)
+__device__ __forceinline__ float u2f(uint32_t x) {
+  float r;
+  asm("cvt.rn.f32.u32 %0, %1;" : "=f"(r) : "r"(x));
+  return r;
+}
 __device__ __forceinline__ uint32_t sat_rz_u8(float x) {
   uint32_t r;
   asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(r) : "f"(x));  // truncate, saturate
@@ -518,11 +525,11 @@ __device__ __forceinline__ void enhance_rgb(int& cr, int& cg, int& cb, const Sme
   const int bb = clampi(ds(200 * (fY - fZ) + 128 * 32768, 15), 0, 255);
   float p00, p01, p10, p11;
   if constexpr (LUTS) {
-    p00 = (float)lut[l1 + ctx1 + L], p01 = (float)lut[l1 + ctx2 + L];
-    p10 = (float)lut[l2 + ctx1 + L], p11 = (float)lut[l2 + ctx2 + L];
+    p00 = u2f(lut[l1 + ctx1 + L]), p01 = u2f(lut[l1 + ctx2 + L]);
+    p10 = u2f(lut[l2 + ctx1 + L]), p11 = u2f(lut[l2 + ctx2 + L]);
   } else {
-    p00 = (float)__ldg(lut + l1 + ctx1 + L), p01 = (float)__ldg(lut + l1 + ctx2 + L);
-    p10 = (float)__ldg(lut + l2 + ctx1 + L), p11 = (float)__ldg(lut + l2 + ctx2 + L);
+    p00 = u2f(__ldg(lut + l1 + ctx1 + L)), p01 = u2f(__ldg(lut + l1 + ctx2 + L));
+    p10 = u2f(__ldg(lut + l2 + ctx1 + L)), p11 = u2f(__ldg(lut + l2 + ctx2 + L));
   }
   const float cxa1 = __fsub_rn(1.0f, cxa);
   const float top = __fadd_rn(__fmul_rn(p00, cxa1), __fmul_rn(p01, cxa));
@@ -795,9 +802,9 @@ post_march_kernel(ImgView img, OutView out, const WowsrTables* __restrict__ tabs
 #pragma unroll
               for (int kk = 0; kk < NPAIR; kk++)
                 if (kk >= k_lo && kk <= k_hi) acc = __dp2a_lo(P[c][kk], m.hw[j][kk], acc);
-              const float blur = (float)(acc >> 16);
+              const float blur = u2f(acc >> 16);
               const uint32_t cw = cen[c][j >> 1];
-              const float cv = (float)((j & 1) ? (cw >> 16) : (cw & 0xFFFFu));
+              const float cv = u2f((j & 1) ? (cw >> 16) : (cw & 0xFFFFu));
               res[c] = sat_rn_u8(__fadd_rn(__fmul_rn(cv, k.alpha), __fmul_rn(blur, k.beta)));
             }
             o[j] = res[0] | (res[1] << 8) | (res[2] << 16);
