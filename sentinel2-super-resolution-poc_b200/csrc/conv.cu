@@ -48,7 +48,7 @@ struct ConvNet {
   std::vector<LayerW> layers;
   DevBuf dense0, dense1, feat, trunk, rrdb, lo, up1, hra, hrb, wins, winxy, err;
   // rolling kernel: task lists per launch geometry (roll_plan_get)
-  struct RollPlanDev { int key[6]; DevBuf tasks, off; int units, units_h; };
+  struct RollPlanDev { int key[7]; DevBuf tasks, off; int units, units_h; };
   std::vector<RollPlanDev> roll_plans;
 };
 
@@ -320,7 +320,7 @@ struct RollPlanHost {
   int units = 0, units_h = 0;
 };
 
-void roll_plan_build(RollPlanHost& R, int Nw, int h, int w, int strip_x0, bool pair, int max_units) {
+void roll_plan_build(RollPlanHost& R, int Nw, int h, int w, int strip_x0, bool pair, int max_units, int v_weight_pm = 1000) {
   struct Col { int n, u0; };
   std::vector<Col> ch, cv;
   const int runs_h = (strip_x0 + TC_RUN - 1) / TC_RUN, rem = w - strip_x0, runs_v = rem > 0 ? (h + TC_RUN - 1) / TC_RUN : 0;
@@ -330,7 +330,10 @@ void roll_plan_build(RollPlanHost& R, int Nw, int h, int w, int strip_x0, bool p
   }
   const int per = pair ? 2 : 1;
   const long long pc_h = ((long long)ch.size() + per - 1) / per, pc_v = ((long long)cv.size() + per - 1) / per;  // (pair-)columns
-  const long long cost_h = pc_h * (h + 4), cost_v = pc_v * (rem + 4);
+  // v_weight_pm (per mille): how much slower a row of a vertical task is than a row of a horizontal one for this layer.  Measured
+  // on full cfg5 batches (profiles/r02_roll_balance_cfg5b.txt): 1.27 for conv_last (64 -> 3 at 4x: HBM-bound, and the transposed
+  // runs read 128 different image rows per box), within +-8 % of 1 for every other layer.
+  const long long cost_h = pc_h * (h + 4), cost_v = pc_v * (rem + 4) * v_weight_pm / 1000;
   // Do not cut segments shorter than this: each costs 2 extra input rows + a junk pair.  Small launches (fewer than 8 rows per
   // unit, e.g. one 128 x 128 tile) are bound by the LATENCY of a unit's groups (~2 us each), not by throughput, and the SMs a
   // longer minimum would leave idle do the extra rows for free: 128 rows over 64 units of 2 rows instead of 13 units of 10
@@ -397,13 +400,13 @@ void roll_plan_build(RollPlanHost& R, int Nw, int h, int w, int strip_x0, bool p
   R.units = units_h + units_v;
 }
 
-int roll_plan_get(wowsr_ctx* ctx, ConvNet* net, int Nw, int h, int w, int strip_x0, bool pair, int max_units,
+int roll_plan_get(wowsr_ctx* ctx, ConvNet* net, int Nw, int h, int w, int strip_x0, bool pair, int max_units, int v_weight_pm,
                   const ConvNet::RollPlanDev** out, cudaStream_t st) {
-  const int key[6] = {Nw, h, w, strip_x0, pair ? 1 : 0, max_units};
+  const int key[7] = {Nw, h, w, strip_x0, pair ? 1 : 0, max_units, v_weight_pm};
   for (const auto& rp : net->roll_plans)
     if (memcmp(rp.key, key, sizeof key) == 0) { *out = &rp; return 0; }
   RollPlanHost H;
-  roll_plan_build(H, Nw, h, w, strip_x0, pair, max_units);
+  roll_plan_build(H, Nw, h, w, strip_x0, pair, max_units, v_weight_pm);
   if (H.units < 1 || H.tasks.empty()) return wowsr_fail(ctx, WOWSR_ERR_ARG, "rolling plan: nothing to do");
   if (net->roll_plans.size() >= 16) {  // shapes change rarely (one per window size and layer resolution); keep the table small
     for (auto& rp : net->roll_plans) { if (rp.tasks.p) cudaFree(rp.tasks.p); if (rp.off.p) cudaFree(rp.off.p); }
@@ -496,7 +499,7 @@ int run_conv_roll(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& 
   const bool strip = rem > 0 && wm > 0 && io.h >= 64 && max_units >= 2 && !wowsr_opt(ctx, "tc_no_strip", 0);
   const int strip_x0 = strip ? wm : io.w;
   const ConvNet::RollPlanDev* plan = nullptr;
-  if (int e = roll_plan_get(ctx, net, io.Nw, io.h, io.w, strip_x0, pair, max_units, &plan, st)) return e;
+  if (int e = roll_plan_get(ctx, net, io.Nw, io.h, io.w, strip_x0, pair, max_units, io.final ? 1270 : 1000, &plan, st)) return e;
   CUtensorMap tmap, tmap_v, tmap32, tmap_v32;
   const bool has_half = L.cin % 64 == 32;
   if (io.in_ups) {

@@ -228,6 +228,7 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_con
   if constexpr (PAIR) ptx::cluster_sync();  // both CTAs' weight halves are in place before the leader issues
   ptx::tc_fence_after();
   if (tr_ph) P.trace[18] = tr_now();
+  if (P.trace != nullptr && threadIdx.x == 0 && blockIdx.x < 148) P.trace[64 + blockIdx.x] = tr_now();
 
   if (warp == TC_WARP_TMA) {
     // ===================== TMA producer: one 2-row box per (stage, chunk) =====================
@@ -599,4 +600,12 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_con
     else ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }
   if (tr_ph) P.trace[20] = tr_now();
+  // debug: when every CTA of the traced launch starts its roles and leaves (ns after CTA 0's entry is subtracted by the tool):
+  // load balance of the work list, horizontal against vertical units
+  if (P.trace != nullptr && threadIdx.x == 0 && blockIdx.x < 148) {
+    P.trace[64 + 148 + blockIdx.x] = tr_now();
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    P.trace[64 + 296 + blockIdx.x] = smid;
+  }
 }
