@@ -48,8 +48,19 @@ struct ConvNet {
   std::vector<LayerW> layers;
   DevBuf dense0, dense1, feat, trunk, rrdb, lo, up1, hra, hrb, wins, winxy, err;
   // rolling kernel: task lists per launch geometry (roll_plan_get)
-  struct RollPlanDev { int key[7]; DevBuf tasks, off; int units, units_h; };
+  struct RollPlanDev { int key[9]; DevBuf tasks, off; int units, units_h; std::vector<int> unit_cost; };
   std::vector<RollPlanDev> roll_plans;
+  // Measured-speed balancing (balance_update): per conv layer, the relative speed of every unit (CTA pair) on that layer as the
+  // kernel timed it in the previous batches, and what the current batch launched.
+  struct Balance {
+    std::vector<float> speed;  // [units], mean 1 within the horizontal and within the vertical units; empty: not measured yet
+    int obs = 0, version = 0;
+    int plan = -1;             // index into roll_plans of the plan launched in this batch (-1: none / not a rolling launch)
+    bool pair = false;
+  };
+  std::vector<Balance> balance;  // [layers]
+  DevBuf unit_ns;                // [layers][160] nanoseconds, written by the kernels
+  std::vector<long long> unit_ns_host;
 };
 
 void wowsr_net_free(ConvNet* n) {
@@ -70,7 +81,7 @@ void wowsr_net_free(ConvNet* n) {
     if (rp.tasks.p) cudaFree(rp.tasks.p);
     if (rp.off.p) cudaFree(rp.off.p);
   }
-  DevBuf* bufs[] = {&n->dense0, &n->dense1, &n->feat, &n->trunk, &n->rrdb, &n->lo, &n->up1, &n->hra, &n->hrb, &n->wins, &n->winxy, &n->err};
+  DevBuf* bufs[] = {&n->dense0, &n->dense1, &n->feat, &n->trunk, &n->rrdb, &n->lo, &n->up1, &n->hra, &n->hrb, &n->wins, &n->winxy, &n->err, &n->unit_ns};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   delete n;
@@ -320,7 +331,8 @@ struct RollPlanHost {
   int units = 0, units_h = 0;
 };
 
-void roll_plan_build(RollPlanHost& R, int Nw, int h, int w, int strip_x0, bool pair, int max_units, int v_weight_pm = 1000) {
+void roll_plan_build(RollPlanHost& R, int Nw, int h, int w, int strip_x0, bool pair, int max_units, int v_weight_pm = 1000,
+                     const float* speed = nullptr /* [max_units] relative speed of every unit, or null: equal shares */) {
   struct Col { int n, u0; };
   std::vector<Col> ch, cv;
   const int runs_h = (strip_x0 + TC_RUN - 1) / TC_RUN, rem = w - strip_x0, runs_v = rem > 0 ? (h + TC_RUN - 1) / TC_RUN : 0;
@@ -364,12 +376,16 @@ void roll_plan_build(RollPlanHost& R, int Nw, int h, int w, int strip_x0, bool p
   }
   R.tasks.clear();
   R.off.assign(1, 0);
-  auto cut = [&](const std::vector<Col>& cols, long long pcs, int len, int v_first, int units) {
+  auto cut = [&](const std::vector<Col>& cols, long long pcs, int len, int v_first, int units, int unit0) {
     if (units <= 0) return;
     const long long total = pcs * len;
     long long done = 0;
+    double wsum = 0.0, wacc = 0.0;
+    for (int k = 0; k < units; k++) wsum += speed ? (double)speed[unit0 + k] : 1.0;
     for (int k = 0; k < units; k++) {
-      const long long end = total * (k + 1) / units;  // exclusive end of this unit's share of the row sequence
+      // exclusive end of this unit's share of the row sequence: equal shares, or shares in proportion to the measured speeds
+      wacc += speed ? (double)speed[unit0 + k] : 1.0;
+      const long long end = k + 1 == units ? total : std::min<long long>(total, (long long)((double)total * wacc / wsum + 0.5));
       while (done < end) {
         const long long pcix = done / len;
         const int r0 = (int)(done - pcix * len);
@@ -394,28 +410,35 @@ void roll_plan_build(RollPlanHost& R, int Nw, int h, int w, int strip_x0, bool p
       R.off.push_back((int)R.tasks.size());
     }
   };
-  cut(ch, pc_h, h, 0, units_h);
-  cut(cv, pc_v, rem, strip_x0, units_v);
+  cut(ch, pc_h, h, 0, units_h, 0);
+  cut(cv, pc_v, rem, strip_x0, units_v, units_h);
   R.units_h = units_h;
   R.units = units_h + units_v;
 }
 
 int roll_plan_get(wowsr_ctx* ctx, ConvNet* net, int Nw, int h, int w, int strip_x0, bool pair, int max_units, int v_weight_pm,
-                  const ConvNet::RollPlanDev** out, cudaStream_t st) {
-  const int key[7] = {Nw, h, w, strip_x0, pair ? 1 : 0, max_units, v_weight_pm};
+                  int bal_layer /* -1: equal shares */, const ConvNet::RollPlanDev** out, cudaStream_t st) {
+  const ConvNet::Balance* B = bal_layer >= 0 && bal_layer < (int)net->balance.size() && (int)net->balance[bal_layer].speed.size() >= max_units
+                                  ? &net->balance[bal_layer] : nullptr;
+  const int key[9] = {Nw, h, w, strip_x0, pair ? 1 : 0, max_units, v_weight_pm, B ? bal_layer + 1 : 0, B ? B->version : 0};
   for (const auto& rp : net->roll_plans)
     if (memcmp(rp.key, key, sizeof key) == 0) { *out = &rp; return 0; }
   RollPlanHost H;
-  roll_plan_build(H, Nw, h, w, strip_x0, pair, max_units, v_weight_pm);
+  roll_plan_build(H, Nw, h, w, strip_x0, pair, max_units, v_weight_pm, B ? B->speed.data() : nullptr);
   if (H.units < 1 || H.tasks.empty()) return wowsr_fail(ctx, WOWSR_ERR_ARG, "rolling plan: nothing to do");
-  if (net->roll_plans.size() >= 16) {  // shapes change rarely (one per window size and layer resolution); keep the table small
+  // one plan per window size and layer resolution, or — once speeds are measured — per layer: a few hundred small lists
+  if (net->roll_plans.size() >= 2048) {
     for (auto& rp : net->roll_plans) { if (rp.tasks.p) cudaFree(rp.tasks.p); if (rp.off.p) cudaFree(rp.off.p); }
     net->roll_plans.clear();
+    for (auto& b : net->balance) b.plan = -1;
   }
   net->roll_plans.emplace_back();
   ConvNet::RollPlanDev& D = net->roll_plans.back();
   memcpy(D.key, key, sizeof key);
   D.units = H.units; D.units_h = H.units_h;
+  D.unit_cost.assign(H.units, 0);
+  for (int u = 0; u < H.units; u++)
+    for (int t = H.off[u]; t < H.off[u + 1]; t++) D.unit_cost[u] += H.tasks[t].rows + 4;
   if (int e = wowsr_ensure(ctx, D.tasks, H.tasks.size() * sizeof(RollTask))) return e;
   if (int e = wowsr_ensure(ctx, D.off, H.off.size() * sizeof(int))) return e;
   WCUDA(ctx, cudaMemcpyAsync(D.tasks.p, H.tasks.data(), H.tasks.size() * sizeof(RollTask), cudaMemcpyHostToDevice, st));
@@ -499,7 +522,25 @@ int run_conv_roll(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& 
   const bool strip = rem > 0 && wm > 0 && io.h >= 64 && max_units >= 2 && !wowsr_opt(ctx, "tc_no_strip", 0);
   const int strip_x0 = strip ? wm : io.w;
   const ConvNet::RollPlanDev* plan = nullptr;
-  if (int e = roll_plan_get(ctx, net, io.Nw, io.h, io.w, strip_x0, pair, max_units, io.final ? 1270 : 1000, &plan, st)) return e;
+  // Measured-speed balancing (option roll_adapt = 1; OFF by default): big launches are timed per CTA, and the next batches cut this
+  // layer's work list in proportion to what every CTA pair achieved on it (balance_update).  Results do not depend on the cuts.
+  // Measured (tools/experiments/r2_adapt*.sh): mean / max of the unit finish times of a full cfg5 batch goes from 0.83-0.95 to
+  // 0.97-0.99 on rdb.conv2, conv_up1 and conv_hr — worth 3-5 % at full clocks — but a full-size step runs under the 1 kW power cap,
+  // where the SMs that used to wait at the end of a launch were saving the power the others ran on: cfg2 -0.85 %, cfg5 scene flat.
+  const int li = (int)(&L - net->layers.data());
+  const bool li_ok = li >= 0 && li < (int)net->layers.size();
+  const bool adapt = li_ok && wowsr_opt(ctx, "roll_adapt", 0) != 0;
+  if (adapt && net->balance.size() != net->layers.size()) {
+    net->balance.assign(net->layers.size(), ConvNet::Balance());
+    if (int e = wowsr_ensure(ctx, net->unit_ns, net->layers.size() * 160 * sizeof(long long))) return e;
+    WCUDA(ctx, cudaMemsetAsync(net->unit_ns.p, 0, net->layers.size() * 160 * sizeof(long long), st));
+  }
+  if (int e = roll_plan_get(ctx, net, io.Nw, io.h, io.w, strip_x0, pair, max_units, io.final ? 1270 : 1000, adapt ? li : -1, &plan, st)) return e;
+  if (adapt) {
+    ConvNet::Balance& B = net->balance[li];
+    B.plan = (int)(plan - net->roll_plans.data());
+    B.pair = pair;
+  }
   CUtensorMap tmap, tmap_v, tmap32, tmap_v32;
   const bool has_half = L.cin % 64 == 32;
   if (io.in_ups) {
@@ -519,6 +560,7 @@ int run_conv_roll(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& 
   RollParams Q;
   memset(&Q, 0, sizeof Q);
   Q.tasks = (const RollTask*)plan->tasks.p;
+  Q.unit_ns = adapt ? (long long*)net->unit_ns.p + (size_t)li * 160 : nullptr;
   Q.task_off = (const int*)plan->off.p;
   Q.units_h = plan->units_h;
   Q.w_bytes = (int)w_need(pair);
@@ -726,6 +768,57 @@ int run_conv(wowsr_ctx* ctx, ConvNet* net, const LayerW& L, const LayerIO& io, c
   else TC_LAUNCH(64, EPI_GENERIC);
 #undef TC_LAUNCH
   WLAUNCH_CHECK(ctx);
+  return 0;
+}
+
+// After a batch (the stream is idle): turns the per-CTA role times of every rolling launch of the batch into relative unit speeds of
+// that layer.  The SMs do not get equal memory bandwidth — on the bandwidth-heavy layers the same 3-4 of every 8 SM pairs finish
+// 15-25 % later, which pairs differs from chip to chip (profiles/r02_roll_balance_*.txt) — so equal rows are not equal time.  The
+// first measurement is taken as it is, later ones are averaged in; after four batches a layer's shares are frozen.
+int balance_update(wowsr_ctx* ctx, ConvNet* net) {
+  if (net->balance.empty() || !net->unit_ns.p) return 0;
+  bool any = false;
+  for (const auto& b : net->balance) any |= b.plan >= 0 && b.obs < 4;
+  if (!any) {
+    for (auto& b : net->balance) b.plan = -1;
+    return 0;
+  }
+  net->unit_ns_host.resize(net->balance.size() * 160);
+  WCUDA(ctx, cudaMemcpy(net->unit_ns_host.data(), net->unit_ns.p, net->unit_ns_host.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+  for (size_t li = 0; li < net->balance.size(); li++) {
+    ConvNet::Balance& B = net->balance[li];
+    const int pi = B.plan;
+    B.plan = -1;
+    if (pi < 0 || pi >= (int)net->roll_plans.size() || B.obs >= 4) continue;
+    const ConvNet::RollPlanDev& D = net->roll_plans[pi];
+    const long long* ns = net->unit_ns_host.data() + li * 160;
+    const int per = B.pair ? 2 : 1, units = D.units;
+    if (units * per > 160 || units < 2) continue;
+    std::vector<double> rate(units, 0.0);
+    bool ok = true;
+    long long cost_min = 1 << 30;
+    for (int u = 0; u < units && ok; u++) {
+      long long t = 0;
+      for (int q = 0; q < per; q++) t = std::max(t, ns[u * per + q]);
+      cost_min = std::min<long long>(cost_min, D.unit_cost[u]);
+      if (t < 20000 || D.unit_cost[u] <= 0) ok = false;  // a unit without work, or a launch too short to time (< 20 us)
+      else rate[u] = (double)D.unit_cost[u] / (double)t;
+    }
+    if (!ok || cost_min < 64) continue;
+    for (int g = 0; g < 2; g++) {  // horizontal and vertical units are separate groups (their split is the cost model's)
+      const int a = g ? D.units_h : 0, b = g ? units : D.units_h;
+      if (b <= a) continue;
+      double mean = 0.0;
+      for (int u = a; u < b; u++) mean += rate[u];
+      mean /= (b - a);
+      for (int u = a; u < b; u++) rate[u] = std::min(1.5, std::max(0.6, rate[u] / mean));
+    }
+    const int max_units = D.key[5];
+    if ((int)B.speed.size() != max_units) { B.speed.assign(max_units, 1.0f); B.obs = 0; }
+    for (int u = 0; u < units; u++) B.speed[u] = B.obs == 0 ? (float)rate[u] : 0.5f * B.speed[u] + 0.5f * (float)rate[u];
+    B.obs++;
+    B.version++;
+  }
   return 0;
 }
 
@@ -977,6 +1070,7 @@ static int forward_windows_impl(wowsr_ctx* ctx, const uint8_t* img_dev, int32_t 
       sent_rows = final_rows;
     }
     if (int e = check_err_flag(ctx, ctx->net, st)) return e;
+    if (int e = balance_update(ctx, ctx->net)) return e;
     if (sink) final_rows = first_row[i0 + nb];
     float a = 0, b = 0, c = 0;
     cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
@@ -1273,6 +1367,7 @@ static int edsr_forward(wowsr_ctx* ctx, ConvNet* net, const uint8_t* img_dev, in
   }
   WCUDA(ctx, cudaEventRecord(ctx->ev[3], st));
   if (int e = check_err_flag(ctx, net, st)) return e;  // synchronises the stream
+  if (int e = balance_update(ctx, net)) return e;
   float t0 = 0, t1 = 0, t2 = 0;
   cudaEventElapsedTime(&t0, ctx->ev[0], ctx->ev[1]);
   cudaEventElapsedTime(&t1, ctx->ev[1], ctx->ev[2]);

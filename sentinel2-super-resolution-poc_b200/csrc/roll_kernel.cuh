@@ -50,6 +50,8 @@ struct RollParams {
   // (transposed taps).  Separate fields: a runtime index into a kernel parameter would force a local-memory copy of the struct.
   const uint8_t* wimg0; const uint8_t* wimg1;
   const uint8_t* wimg_v0; const uint8_t* wimg_v1;
+  long long* unit_ns;       // [gridDim.x] (may be null): nanoseconds every CTA spent in its roles; the host rebalances the next batch's
+                            // work list of this layer with them (conv.cu, balance_update)
 };
 
 // Field access by pair rank without materialising the task in local memory.
@@ -228,6 +230,7 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_con
   if constexpr (PAIR) ptx::cluster_sync();  // both CTAs' weight halves are in place before the leader issues
   ptx::tc_fence_after();
   if (tr_ph) P.trace[18] = tr_now();
+  const long long ns0 = (Q.unit_ns != nullptr && threadIdx.x == 0) ? tr_now() : 0;
   if (P.trace != nullptr && threadIdx.x == 0 && blockIdx.x < 148) P.trace[64 + blockIdx.x] = tr_now();
 
   if (warp == TC_WARP_TMA) {
@@ -594,6 +597,7 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_con
   ptx::tc_fence_before();
   __syncthreads();
   if (tr_ph) P.trace[19] = tr_now();
+  if (Q.unit_ns != nullptr && threadIdx.x == 0) Q.unit_ns[blockIdx.x] = tr_now() - ns0;
   if constexpr (PAIR) ptx::cluster_sync();  // the peer's shared memory and barriers stay alive until both CTAs are done
   if (warp == TC_WARP_MMA) {
     if constexpr (PAIR) ptx::tmem_dealloc_pair(tmem_base, TMEM_COLS);

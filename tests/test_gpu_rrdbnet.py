@@ -331,3 +331,20 @@ def test_folded_upsample_is_bit_identical_to_replicated_store(ws):
                 outs.append(h.enhance_host(img, tile, want_float=True))
                 h.close()
             assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]), (roll, shape, tile)
+
+
+def test_measured_speed_balancing_keeps_results_bit_identical(ws):
+    """The rolling kernel's work lists are re-cut from the measured unit speeds over the first batches (conv.cu, balance_update;
+    option roll_adapt = 1, off by default): every run of the same input must give the same bytes as the run with equal shares."""
+    blocks = 2
+    sd = R.random_init_state_dict(5, blocks)
+    img = np.random.default_rng(5).integers(0, 256, (1000, 1100, 3), dtype=np.uint8)      # 4 x 5 windows of 276: launches long enough to time
+    h0 = ws.Handle(0)
+    h0.set_option("roll_adapt", 0)
+    h0.load_rrdbnet(_tensors(sd, blocks), blocks, precision="bf16")
+    want = h0.enhance_host(img, 256)
+    h1 = ws.Handle(0)
+    h1.set_option("roll_adapt", 1)
+    h1.load_rrdbnet(_tensors(sd, blocks), blocks, precision="bf16")
+    for i in range(6):
+        assert np.array_equal(h1.enhance_host(img, 256), want), f"run {i}"
