@@ -13,6 +13,12 @@
 #include "ups_kernel.cuh"
 #include "roll_kernel.cuh"
 
+// Default of option `pdl` (programmatic dependent launch of the rolling kernel, roll_launch).  A build flag so that an A/B
+// library (WOWSR_LIB) can run the whole test suite with the other default.
+#ifndef WOWSR_PDL_DEFAULT
+#define WOWSR_PDL_DEFAULT 1
+#endif
+
 namespace {
 
 constexpr size_t SMEM_LIMIT = 232448;  // 227 KB opt-in maximum per block on sm_100
@@ -463,13 +469,22 @@ int roll_launch(wowsr_ctx* ctx, int grid, size_t smem, cudaStream_t st, const CU
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = PAIR ? 2 : 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  // Programmatic dependent launch: this launch may start while the previous kernel of the stream drains; the kernel reads and
+  // writes activations only after griddepcontrol.wait (roll_kernel.cuh).  Small launches gain the most (cfg1: 354 dependent
+  // launches of 7-17 us, each with 2.3-3 us of set-up and a launch gap).  Off while a layer is traced (the phase stamps of two
+  // launches would interleave).
+  if (wowsr_opt(ctx, "pdl", WOWSR_PDL_DEFAULT) != 0 && P.trace == nullptr) {
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   WCUDA(ctx, cudaLaunchKernelEx(&cfg, kern, th, tv, th32, tv32, P, Q));
   ctx->launches++;
   return 0;

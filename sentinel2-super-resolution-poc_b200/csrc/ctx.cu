@@ -276,7 +276,7 @@ extern "C" uint64_t wowsr_launch_count(const wowsr_ctx* ctx) { return ctx ? ctx-
 static const char* const kOptionKeys[] = {
     "conv_impl",   "hist_match", "mem_budget_mb",       "tc_boustrophedon", "tc_chunk32", "tc_flags",
     "tc_force_stream", "tc_generic_epilogue", "tc_grid", "tc_no_strip", "tc_stages", "tc_trace_layer",
-    "tc_wbuf",     "trunk_hilo", "tail_fold_upsample",  "roll", "roll_pair", "roll_grid", "roll_ups", "hsv_simd_width", "post_kernel", "post_nt", "post_seg", "post_groups", "roll_adapt"};
+    "tc_wbuf",     "trunk_hilo", "tail_fold_upsample",  "roll", "roll_pair", "roll_grid", "roll_ups", "hsv_simd_width", "post_kernel", "post_nt", "post_seg", "post_groups", "roll_adapt", "pdl"};
 
 extern "C" int wowsr_set_option(wowsr_ctx* ctx, const char* key, int64_t value) {
   if (!ctx || !key) return WOWSR_ERR_ARG;

@@ -175,6 +175,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- programmatic dependent launch (cudaLaunchAttributeProgrammaticStreamSerialization) ------------
+// launch_dependents: the next kernel of the stream may start its CTAs as soon as every CTA of this grid has got here (or left)
+// and an SM has room.  wait: blocks until every grid this one depends on has COMPLETED and its memory is visible — nothing the
+// previous kernel wrote may be read, and nothing it reads may be written, before this.  Both are no-ops in a launch without
+// the attribute.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- CTA pairs (cluster of 2, tcgen05 cta_group::2) ---------------------------------------------
 // Forms follow the PTX ISA and the vendored CUTLASS headers (cute/arch/copy_sm100_tma.hpp SM100_TMA_2SM_LOAD_4D,
 // cutlass/arch/barrier.h umma_arrive_multicast_2x1SM, cute/arch/tmem_allocator_sm100.hpp Allocator2Sm); no CUTLASS code is used.

@@ -154,6 +154,10 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_con
   const bool tr_ph = P.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
   auto tr_now = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (long long)t; };
   if (tr_ph) P.trace[16] = tr_now();
+  // Programmatic dependent launch (conv.cu roll_launch, option pdl): the next layer's CTAs may take SMs as this launch's CTAs
+  // leave and run their set-up — barriers, TMEM, resident weights, none of which depends on a previous layer — under this
+  // launch's tail.  Everything a previous layer wrote is first touched after griddep_wait() below.
+  ptx::griddep_launch_dependents();
   const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const bool vert = unit >= Q.units_h;
   const CUtensorMap& tmap = vert ? tmap_v : tmap_h;
@@ -229,6 +233,7 @@ conv3x3_roll_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_con
   __syncthreads();
   if constexpr (PAIR) ptx::cluster_sync();  // both CTAs' weight halves are in place before the leader issues
   ptx::tc_fence_after();
+  ptx::griddep_wait();  // the previous layer has completed: activations may be read, outputs written
   if (tr_ph) P.trace[18] = tr_now();
   const long long ns0 = (Q.unit_ns != nullptr && threadIdx.x == 0) ? tr_now() : 0;
   if (P.trace != nullptr && threadIdx.x == 0 && blockIdx.x < 148) P.trace[64 + blockIdx.x] = tr_now();
