@@ -348,3 +348,25 @@ def test_measured_speed_balancing_keeps_results_bit_identical(ws):
     h1.load_rrdbnet(_tensors(sd, blocks), blocks, precision="bf16")
     for i in range(6):
         assert np.array_equal(h1.enhance_host(img, 256), want), f"run {i}"
+
+
+def test_programmatic_dependent_launch_keeps_results_bit_identical(ws):
+    """The conv launches overlap a layer's set-up with the previous layer's tail (option pdl, default on: griddepcontrol.wait
+    sits between the set-up and the first access to an activation, roll_kernel.cuh).  A missed dependency would show as stale
+    reads in the small launches, where a layer's CTAs start while the previous layer still runs: small and mid-size inputs, several
+    runs each, must give the bytes of the fully serialised launches."""
+    blocks = 3
+    sd = R.calibrate_conv_last(R.random_init_state_dict(6, blocks), blocks)
+    h0, h1 = ws.Handle(0), ws.Handle(0)
+    h0.set_option("pdl", 0)
+    h1.set_option("pdl", 1)
+    for h in (h0, h1):
+        h.load_rrdbnet(_tensors(sd, blocks), blocks, precision="bf16")
+    for shape, tile in (((128, 128), 256), ((64, 200), 256), ((300, 420), 128)):
+        img = np.random.default_rng(21).integers(0, 256, shape + (3,), dtype=np.uint8)
+        want_u8, want_f = h0.enhance_host(img, tile, want_float=True)
+        for i in range(4):
+            u8, f = h1.enhance_host(img, tile, want_float=True)
+            assert np.array_equal(u8, want_u8) and np.array_equal(f, want_f), (shape, tile, i)
+    h0.close()
+    h1.close()
