@@ -316,7 +316,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    conv_ms = []
+    conv_ms, enq_ms = [], []
     barrier()
     ev0.record()
     for _ in range(args.steps):
@@ -324,6 +324,7 @@ def run_ours(args):
         if tile > 0:
             t = h.timing()
             conv_ms.append(t["head"] + t["trunk"] + t["tail"])   # conv_first + RRDB trunk + HR tail: every conv launch of the step
+            enq_ms.append(t.get("enqueue_host", 0.0))            # host time of the thread that enqueued them
     ev1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -446,7 +447,8 @@ def run_ours(args):
                 "achieved": ach, "peak": pk["bf16_tflops_sustained"], "peak_burst": pk["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": ach / pk["bf16_tflops_sustained"], "frac_of_burst": ach / pk["bf16_tflops"], "peak_source": pk["src"],
                 "traffic": traffic, "traffic_note": traffic_note,
-                "conv_ms_per_step": conv_t * 1e3, "algorithmic_flops_per_step": per_rank_flops}
+                "conv_ms_per_step": conv_t * 1e3, "algorithmic_flops_per_step": per_rank_flops,
+                "host_enqueue_ms_per_step": sum(enq_ms) / max(len(enq_ms), 1)}
     else:
         ach = OH * OW * POST_BYTES_PER_PX / (ms / 1e3) / 1e9
         roof = {"bound": "hbm", "kernel": "clahe_hist + post_apply", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",

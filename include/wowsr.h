@@ -210,7 +210,8 @@ int wowsr_conv3x3_host(wowsr_ctx* ctx, const float* in, int32_t n, int32_t h, in
                        int32_t cin, const float* weight, const float* bias, int32_t cout,
                        int32_t act, int32_t precision, float* out);
 /* Timing of the last forward (CUDA events on the handle's stream): milliseconds per phase.
- * phases: 0 total, 1 head, 2 trunk (RRDBs), 3 tail (HR convs). Returns count written. */
+ * phases: 0 total, 1 head, 2 trunk (RRDBs), 3 tail (HR convs); 4 = HOST milliseconds the calling thread spent enqueuing the
+ * forward's launches (wowsr_rrdbnet_forward_windows / wowsr_enhance_*; 0 for EDSR).  Returns count written (<= cap). */
 int32_t wowsr_get_timing(const wowsr_ctx* ctx, float* ms, int32_t cap);
 /* Debug: per-tile clock64 stamps [tile][mma_start, mma_issued, epilogue_start, epilogue_end] of CTA 0 of the conv
  * launch selected with wowsr_set_option("tc_trace_layer", k) (k = 1-based launch index). Returns count. */

@@ -158,9 +158,9 @@ class Handle:
         return int(self._L.wowsr_launch_count(self._h))
 
     def timing(self):
-        buf = (C.c_float * 4)()
-        n = self._L.wowsr_get_timing(self._h, buf, 4)
-        return dict(zip(("total", "head", "trunk", "tail"), list(buf)[:n]))
+        buf = (C.c_float * 5)()
+        n = self._L.wowsr_get_timing(self._h, buf, 5)
+        return dict(zip(("total", "head", "trunk", "tail", "enqueue_host"), list(buf)[:n]))
 
     def debug_trace(self):
         buf = (C.c_int64 * 512)()  # rows 0..63: tile timeline; rows 64..127: epilogue breakdown (instrumented builds)

@@ -6,6 +6,7 @@
 #include <cudaTypedefs.h>
 
 #include <algorithm>
+#include <chrono>
 
 #include "common.h"
 #include "hoststage.h"
@@ -1066,6 +1067,8 @@ static int forward_windows_impl(wowsr_ctx* ctx, const uint8_t* img_dev, int32_t 
   int nbatches = (n + maxb - 1) / maxb;
   int per = (n + nbatches - 1) / nbatches;
   float t_head = 0, t_trunk = 0, t_tail = 0;
+  double t_enqueue = 0;  // host wall time inside rrdbnet_batch: buffers, window table, 350 launches — against the event times it
+                         // tells whether a small forward (cfg1) is bound by the device or by the launching thread
   // suffix minimum of the first output row a window owns: after the windows before i are done, no later window writes above it
   std::vector<int> first_row;
   if (sink) {
@@ -1078,8 +1081,10 @@ static int forward_windows_impl(wowsr_ctx* ctx, const uint8_t* img_dev, int32_t 
   int sent_rows = 0, final_rows = 0;
   for (int i0 = 0; i0 < n; i0 += per) {
     int nb = std::min(per, n - i0);
+    const auto tq0 = std::chrono::steady_clock::now();
     if (int e = rrdbnet_batch(ctx, ctx->net, img_dev, pitch, windows + i0, nb, out_dev, out_pitch, out_f32, out_f32_pitch, st))
       return e;
+    t_enqueue += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tq0).count();
     if (sink && final_rows > sent_rows) {  // rows the PREVIOUS batches completed leave while this batch computes
       sink->enqueue(out_dev, (size_t)out_pitch, sent_rows, final_rows, nullptr);
       sent_rows = final_rows;
@@ -1096,6 +1101,7 @@ static int forward_windows_impl(wowsr_ctx* ctx, const uint8_t* img_dev, int32_t 
   if (sink) sink->enqueue(out_dev, (size_t)out_pitch, sent_rows, 4 * H, nullptr);
   ctx->timing[0] = t_head + t_trunk + t_tail;
   ctx->timing[1] = t_head; ctx->timing[2] = t_trunk; ctx->timing[3] = t_tail;
+  ctx->timing[4] = (float)t_enqueue;
   return WOWSR_OK;
 }
 
@@ -1173,7 +1179,7 @@ extern "C" int32_t wowsr_debug_roll_plan(int32_t n_win, int32_t h, int32_t w, in
 
 extern "C" int32_t wowsr_get_timing(const wowsr_ctx* ctx, float* ms, int32_t cap) {
   if (!ctx || !ms) return WOWSR_ERR_ARG;
-  int n = cap < 4 ? cap : 4;
+  int n = cap < 5 ? cap : 5;
   for (int i = 0; i < n; i++) ms[i] = ctx->timing[i];
   return n;
 }
@@ -1388,6 +1394,7 @@ static int edsr_forward(wowsr_ctx* ctx, ConvNet* net, const uint8_t* img_dev, in
   cudaEventElapsedTime(&t1, ctx->ev[1], ctx->ev[2]);
   cudaEventElapsedTime(&t2, ctx->ev[2], ctx->ev[3]);
   ctx->timing[0] = t0 + t1 + t2; ctx->timing[1] = t0; ctx->timing[2] = t1; ctx->timing[3] = t2;
+  ctx->timing[4] = 0;
   return WOWSR_OK;
 }
 
